@@ -1,0 +1,151 @@
+/*
+ * libcpab_b200.h -- C ABI of the B200-native CPAB transformation library (libcpab_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of SkafteNicki/libcpab when
+ * backend='pytorch', device='gpu'.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference repository root).  The reference binds its native code through
+ * a pybind11/torch extension (libcpab/pytorch/transformer_cuda.cpp:73-76: forward, backward);
+ * here the same operations are plain C functions over device pointers, callable from ctypes
+ * (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers to contiguous row-major arrays of `dtype`
+ *     (CPAB_F32 = float, CPAB_F64 = double "check mode") on the current device.
+ *   - The caller owns every buffer (outputs and workspace included); the library allocates no
+ *     persistent memory and keeps no state besides the per-thread error string and the tuning
+ *     knobs set through cpab_b200_set_tuning.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and the call returns without synchronising.
+ *   - `nc` points to `ndim` host ints (tessellation size per dimension), ndim in {1,2,3}.
+ *   - Layouts: points/grids are planar [ndim, nP] or
+ *     [n_theta, ndim, nP]; affine parameters are [n_theta, nC, ndim, ndim+1] with
+ *     nC = nx | 4*nx*ny | 5*nx*ny*nz simplices; the basis is [D, d], D = nC*ndim*(ndim+1).
+ *   - Return value: CPAB_OK (0) or a negative CPAB_ERR_* code; cpab_b200_last_error() gives the
+ *     message for the calling thread.  The library never calls exit() (the reference does:
+ *     libcpab/pytorch/transformer_cuda.cu:8-16).
+ */
+#ifndef LIBCPAB_B200_H
+#define LIBCPAB_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPAB_OK               0
+#define CPAB_ERR_ARGUMENT    (-1)
+#define CPAB_ERR_CUDA        (-2)
+#define CPAB_ERR_UNSUPPORTED (-3)
+#define CPAB_ERR_WORKSPACE   (-4)
+
+#define CPAB_F32 0
+#define CPAB_F64 1
+
+/* flags */
+#define CPAB_FLAG_FAST_MATH 1   /* forward: contract a*b+c into FMAs (default: every operation
+                                   rounded as the CPU reference does -> bit-identical results) */
+
+/* ABI revision of this header; bumped on any signature change. */
+int cpab_b200_abi_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* cpab_b200_last_error(void);
+
+/* Compile-time facts: "sm_100a;cuda=12.9;..." */
+const char* cpab_b200_build_info(void);
+
+/* Experiment knobs ("fwd_ppt", "chunk_pts", "bwd_seg", "bwd_block"); results never depend on them
+ * beyond floating-point summation order in the gradient. */
+int cpab_b200_set_tuning(const char* key, int value);
+
+/* Diagnostic: `blocks` CTAs of 256 threads each run `iters` x 64 dependent-chain FP32 FMAs
+ * (8 independent chains per thread).  bench.py times it to obtain the measured FP32 peak that
+ * the integration roofline is quoted against.  `out` is one device float (never written). */
+int cpab_b200_fp32_fma_probe(int blocks, int iters, void* out, void* stream);
+
+/*
+ * Cell index of every point.  Replaces findcellidx, libcpab/core/cpab_ops.cpp:26-190 /
+ * libcpab/core/cpab_ops.cu:14-227 (the index the integrators use), bit-exact with the CPU one.
+ *   points [ndim, nP] -> out_idx int32 [nP]
+ */
+int cpab_b200_findcellidx(int dtype, int ndim, const int* nc, const void* points, long nP,
+                          int* out_idx, void* stream);
+
+/*
+ * theta -> velocity-field matrices and per-step transition matrices.  Replaces
+ * libcpab/pytorch/transformer.py:146-155 (B @ theta^T, reshape, zero-row pad, expm(dT*A)) and
+ * libcpab/pytorch/expm.py:11-54.
+ *   basis_t [d, D] (the basis TRANSPOSED, i.e. the reference's `Bs` tensor, transformer.py:174)
+ *   theta   [n_theta, d]
+ *   As      [n_theta, nC, ndim, ndim+1]  out
+ *   trels   [n_theta, nC, ndim, ndim+1]  out, expm(A/nsteps) top rows
+ */
+int cpab_b200_theta_to_trels(int dtype, int ndim, const int* nc, int nsteps, int n_theta, int d,
+                             const void* basis_t, const void* theta, void* As, void* trels,
+                             void* stream);
+
+/* Batched expm of n (m x m) matrices, m in {2,3,4}; libcpab/pytorch/expm.py:11-36 as an op. */
+int cpab_b200_expm(int dtype, int m, long n, const void* A, void* E, void* stream);
+
+/*
+ * Forward integration.  Replaces cpab_gpu.forward(points, trels, nstepsolver, nc),
+ * libcpab/pytorch/transformer_cuda.cpp:17-41 -> transformer_cuda.cu:18-64 -> core/cpab_ops.cu:268-388.
+ *   points    [ndim, nP] (broadcast=0) or [n_theta, ndim, nP] (broadcast=1)
+ *   trels     [n_theta, nC, ndim, ndim+1]
+ *   newpoints [n_theta, ndim, nP]  out
+ */
+int cpab_b200_forward(int dtype, int flags, int ndim, const int* nc, int nsteps, int n_theta,
+                      long nP, int broadcast, const void* points, const void* trels,
+                      void* newpoints, void* stream);
+
+/*
+ * Reference-layout theta-Jacobian.  Replaces cpab_gpu.backward(points, As, Bs, nstepsolver, nc),
+ * libcpab/pytorch/transformer_cuda.cpp:43-70 -> transformer_cuda.cu:66-119 -> core/cpab_ops.cu:390-697.
+ *   Bs  [d, nC, ndim, ndim+1] (= basis_t)      jac [d, n_theta, ndim, nP]  out
+ * Kept for drop-in completeness and op-level parity; it is d-fold redundant by construction and
+ * limited to n_theta*d <= 65535.  Training code should use cpab_b200_backward_theta.
+ */
+int cpab_b200_backward_jacobian(int dtype, int ndim, const int* nc, int nsteps, int n_theta, int d,
+                                long nP, int broadcast, const void* points, const void* As,
+                                const void* Bs, void* jac, void* stream);
+
+/* Bytes of scratch cpab_b200_backward_theta needs (G, [n_theta, D]). */
+size_t cpab_b200_backward_workspace_bytes(int dtype, int ndim, const int* nc, int n_theta);
+
+/*
+ * dL/dtheta (and optionally dL/dpoints) in one adjoint sweep.  Replaces the pair
+ * cpab_gpu.backward (above) + `gradient.mul_(grad).sum(dim=(2,3))`,
+ * libcpab/pytorch/transformer.py:187-202, without materialising [d, n_theta, ndim, nP].
+ *   points   as in forward          As       [n_theta, nC, ndim, ndim+1]
+ *   basis    [D, d] (row-major, as params.basis)
+ *   grad_out [n_theta, ndim, nP]    dtheta   [n_theta, d]  out
+ *   dpoints  [n_theta, ndim, nP]    out, may be NULL (the reference returns None for it)
+ */
+int cpab_b200_backward_theta(int dtype, int flags, int ndim, const int* nc, int nsteps,
+                             int n_theta, int d, long nP, int broadcast, const void* points,
+                             const void* As, const void* basis, const void* grad_out,
+                             void* dtheta, void* dpoints, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/*
+ * Linear / bilinear / trilinear sampling.  Replaces interpolate(ndim, data, grid, outsize),
+ * libcpab/pytorch/interpolation.py:12-172.
+ *   data [N, C, in_size...]   grid [N, ndim, prod(out_size)]   out [N, C, out_size...]
+ */
+int cpab_b200_interpolate_forward(int dtype, int ndim, int N, int C, const int* in_size,
+                                  const int* out_size, const void* data, const void* grid,
+                                  void* out, void* stream);
+
+/*
+ * Backward of the above (what autograd derives for the reference).  dgrid [N, ndim, nP] and
+ * ddata [N, C, in_size...] are outputs; either may be NULL.  ddata is zeroed by the call.
+ */
+int cpab_b200_interpolate_backward(int dtype, int ndim, int N, int C, const int* in_size,
+                                   const int* out_size, const void* data, const void* grid,
+                                   const void* grad_out, void* dgrid, void* ddata, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBCPAB_B200_H */

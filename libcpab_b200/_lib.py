@@ -1,0 +1,86 @@
+"""ctypes binding of libcpab_b200.so (the C ABI declared in include/libcpab_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing and cannot be built, or a call fails,
+this module raises.  (The reference silently degrades to a pure-python path when its extension
+fails to compile, libcpab/pytorch/transformer.py:39-69; north_star forbids that here.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+_lock = threading.Lock()
+_lib = None
+
+CPAB_F32, CPAB_F64 = 0, 1
+CPAB_FLAG_FAST_MATH = 1
+ABI_VERSION = 1
+
+_vp, _i, _l, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_size_t
+_ip = ctypes.POINTER(ctypes.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/libcpab_b200.h declares
+SIGNATURES = {
+    "cpab_b200_abi_version": (_i, []),
+    "cpab_b200_last_error": (ctypes.c_char_p, []),
+    "cpab_b200_build_info": (ctypes.c_char_p, []),
+    "cpab_b200_set_tuning": (_i, [ctypes.c_char_p, _i]),
+    "cpab_b200_fp32_fma_probe": (_i, [_i, _i, _vp, _vp]),
+    "cpab_b200_findcellidx": (_i, [_i, _i, _ip, _vp, _l, _vp, _vp]),
+    "cpab_b200_theta_to_trels": (_i, [_i, _i, _ip, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cpab_b200_expm": (_i, [_i, _i, _l, _vp, _vp, _vp]),
+    "cpab_b200_forward": (_i, [_i, _i, _i, _ip, _i, _i, _l, _i, _vp, _vp, _vp, _vp]),
+    "cpab_b200_backward_jacobian": (_i, [_i, _i, _ip, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp]),
+    "cpab_b200_backward_workspace_bytes": (_sz, [_i, _i, _ip, _i]),
+    "cpab_b200_backward_theta": (_i, [_i, _i, _i, _ip, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _sz, _vp]),
+    "cpab_b200_interpolate_forward": (_i, [_i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp]),
+    "cpab_b200_interpolate_backward": (_i, [_i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp,
+                                            _vp]),
+}
+
+
+class CpabError(RuntimeError):
+    """A libcpab_b200 call returned a negative status."""
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if the shared object is absent or stale and nvcc is available)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if not os.path.exists(path):
+            _build.build()          # raises if nvcc is missing: no silent fallback
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError = ABI mismatch, surfaced loudly
+            fn.restype = res
+            fn.argtypes = args
+        got = lib.cpab_b200_abi_version()
+        if got != ABI_VERSION:
+            raise CpabError(f"libcpab_b200.so ABI {got} != expected {ABI_VERSION}; rebuild")
+        _lib = lib
+        return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().cpab_b200_last_error().decode()
+        raise CpabError(f"{what} failed with status {status}: {msg}")
+
+
+def nc_array(nc):
+    return (ctypes.c_int * len(nc))(*[int(v) for v in nc])
+
+
+def set_tuning(key: str, value: int) -> None:
+    check(load().cpab_b200_set_tuning(key.encode(), int(value)), "set_tuning")

@@ -1,0 +1,311 @@
+// cpab_cell.cuh -- point -> simplex index ("findcellidx") for 1-D / 2-D / 3-D CPAB tessellations.
+//
+// Replaces libcpab/core/cpab_ops.cpp:26-190 (CPU) and libcpab/core/cpab_ops.cu:14-227 (GPU) of the
+// reference.  The contract is BIT-EXACT agreement with the reference's CPU function on every float
+// input, but the arithmetic is redesigned for the GPU:
+//
+//   * The reference works in double with 6 (2-D) / 9 (3-D) fp64 divisions and an fmod per axis.
+//     fmod is exact, so the reference's column index is floor_exact(p / w) and its remainder is
+//     p - k*w, both of which a single FP32 FMA delivers exactly: estimate k with one FFMA against
+//     a rounding constant, form r = fma(-k, w, p) (exact: r is a multiple of ulp(w) below 2^24
+//     ulps), fix the estimate by the sign of r.  No division, no conversion instruction.
+//   * The triangle / tetrahedron tests compare local coordinates r/w.  They are evaluated in FP32
+//     with a guard band; only a point within the band of a diagonal (or in a corner region outside
+//     the domain) drops to an exact path.  In 2-D the exact path is still division-free (products
+//     of two floats are exact in double); the last resort replays the reference's own double
+//     expression sequence.
+//   * All per-tessellation constants the reference recomputes per call (cell widths rounded to
+//     float, the `n*inc - 1e-9` clamp, the row/column a clamped coordinate falls in) are evaluated
+//     once on the host by make_geom(), literally as the reference writes them.
+//
+// The header compiles for host and device.  The host build is used ONLY by the CPU test harness
+// (tests/harness), which sweeps these functions against the oracle; the product has no CPU path.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define CPAB_HD __host__ __device__ __forceinline__
+#define CPAB_HD_NOINLINE inline __host__ __device__ __noinline__
+#else
+#define CPAB_HD inline
+#define CPAB_HD_NOINLINE inline
+#endif
+
+namespace cpab {
+
+// Tessellation geometry plus host-evaluated constants.  Passed to kernels by value.
+struct Geom {
+    int ndim;
+    int nc[3];
+    int n_cells;        // simplices: nx | 4 nx ny | 5 nx ny nz
+    // ---- float32 path -----------------------------------------------------------------------
+    float nf[3];        // (float)n
+    float w[3];         // cell width rounded to float: `const float inc = 1.0 / n`
+    float span[3];      // (float)(n * inc): the upper domain bound the reference compares with
+    float khi[3];       // 2-D: column/row (already min'ed with n-1) of a coordinate clamped high
+    float hi3[3];       // 3-D: clamp bound (float)(n*inc - 1e-8); z uses inc_x (cpab_ops.cpp:141)
+    // ---- float64 check mode -------------------------------------------------------------------
+    double wd[3];       // 1.0 / n
+    double spand[3];    // n * wd
+    double hi3d[3];     // n*wd - 1e-8, z with wd[0]
+};
+
+CPAB_HD float  abs_t(float x)  { return fabsf(x); }
+CPAB_HD double abs_t(double x) { return fabs(x); }
+CPAB_HD float  sign_t(float m, float s)   { return copysignf(m, s); }
+CPAB_HD double sign_t(double m, double s) { return copysign(m, s); }
+
+// the reference's mymin (cpab_ops.cpp:22-24): `!(b<a) ? a : round(b)`
+CPAB_HD int pick_min(int a, double b) { return (b < (double)a) ? (int)round(b) : a; }
+
+inline Geom make_geom(int ndim, const int* nc)
+{
+    Geom g;
+    memset(&g, 0, sizeof(g));
+    g.ndim = ndim;
+    long cells = ndim == 1 ? 1 : (ndim == 2 ? 4 : 5);
+    for (int j = 0; j < 3; ++j) {
+        const int n = j < ndim ? nc[j] : 1;
+        g.nc[j] = n;
+        if (j < ndim) cells *= n;
+        g.nf[j] = (float)n;
+        g.w[j] = (float)(1.0 / n);
+        g.span[j] = (float)n * g.w[j];                       // int*float -> float multiply
+        g.wd[j] = 1.0 / n;
+        g.spand[j] = n * g.wd[j];
+        // 2-D, coordinate clamped to span - 1e-9 (cpab_ops.cpp:44-45,53-54)
+        const double top = (double)g.span[j] - 0.000000001;
+        const double rem = fmod(top, (double)g.w[j]);
+        g.khi[j] = (float)pick_min(n - 1, (top - rem) / (double)g.w[j]);
+    }
+    g.n_cells = (int)cells;
+    for (int j = 0; j < 3; ++j) {
+        const int wsel = (j == 2) ? 0 : j;                   // sic: nz * inc_x
+        g.hi3[j] = (float)((double)((float)g.nc[j] * g.w[wsel]) - 1e-8);
+        g.hi3d[j] = g.nc[j] * g.wd[wsel] - 1e-8;
+    }
+    return g;
+}
+
+// -------------------------------------------------------------------------------------------------
+// float32 building block: exact floor(p / w) and exact remainder for 0 <= p, p/w < 2^21.
+// kf is returned as a float holding the integer.
+CPAB_HD void divmod_exact(float p, float nf, float w, float& kf, float& r)
+{
+    const float kMagic = 12582912.0f;                       // 1.5 * 2^23: adding it rounds to integer
+    const float t = fmaf(p, nf, kMagic);                    // RN(p*n) in the low mantissa bits
+    kf = t - kMagic;                                        // exact
+    r = fmaf(-kf, w, p);                                    // exact remainder for k in {k*, k*+1}
+    if (r < 0.0f) { kf -= 1.0f; r += w; }                   // estimate was one too high; r+w is exact
+    if (r >= w)   { kf += 1.0f; r = fmaf(-kf, w, p); }      // (only reachable through estimate error)
+}
+
+// ------------------------------------------------------------------------------------------- 1-D
+CPAB_HD int find_cell_1d(float p0, const Geom& g)
+{
+#if defined(__CUDA_ARCH__)
+    const float s = __fmul_rn(p0, g.nf[0]);                 // the reference's float multiply, unfused
+#else
+    const float s = p0 * g.nf[0];
+#endif
+    // floorf then clamp in float (NaN-safe through fminf/fmaxf), one conversion at the end
+    const float c = fminf(fmaxf(floorf(s), 0.0f), g.nf[0] - 1.0f);
+    return (int)c;
+}
+
+CPAB_HD int find_cell_1d(double p0, const Geom& g)
+{
+    int c = (int)floor(p0 * g.nc[0]);
+    c = c > g.nc[0] - 1 ? g.nc[0] - 1 : c;
+    return c < 0 ? 0 : c;
+}
+
+// ------------------------------------------------------------------------------------------- 2-D
+// Literal double replay of cpab_ops.cpp:33-104 for T = float (point widened, widths float) and
+// T = double (everything double).  Used as the last-resort path and as the fp64 check mode.
+template <typename T>
+CPAB_HD_NOINLINE int find_cell_2d_replay(T p0, T p1, const Geom& g)
+{
+    const bool f32 = sizeof(T) == 4;
+    const double qx = p0, qy = p1;
+    const double wx = f32 ? (double)g.w[0] : g.wd[0];
+    const double wy = f32 ? (double)g.w[1] : g.wd[1];
+    const double sx = f32 ? (double)g.span[0] : g.spand[0];
+    const double sy = f32 ? (double)g.span[1] : g.spand[1];
+    const int nx = g.nc[0], ny = g.nc[1];
+    double cx = qx > 0.0 ? qx : 0.0;
+    double cy = qy > 0.0 ? qy : 0.0;
+    if (sx - 0.000000001 < cx) cx = sx - 0.000000001;
+    if (sy - 0.000000001 < cy) cy = sy - 0.000000001;
+    const double rx = fmod(cx, wx), ry = fmod(cy, wy);
+    const double lx = rx / wx, ly = ry / wy;
+    int base = 4 * (pick_min(nx - 1, (cx - rx) / wx) + pick_min(ny - 1, (cy - ry) / wy) * nx);
+    if (qx <= 0) {
+        if (qy <= 0 && qy / wy < qx / wx) return base;
+        if (qy >= sy && qy / wy - ny > -qx / wx) return base + 2;
+        return base + 3;
+    }
+    if (qx >= sx) {
+        if (qy <= 0 && -qy / wy > qx / wx - nx) return base;
+        if (qy >= sy && qy / wy - ny > qx / wx - nx) return base + 2;
+        return base + 1;
+    }
+    if (qy <= 0) return base;
+    if (qy >= sy) return base + 2;
+    if (lx < ly) return (1 - lx < ly) ? base + 2 : base + 3;
+    if (1 - lx < ly) return base + 1;
+    return base;
+}
+
+// In-domain triangle choice from exact remainders, without division where possible.
+//   x = RN(rx/wx), y = RN(ry/wy) in the reference.  rx*wy and ry*wx are products of two floats and
+//   therefore exact in double; distinct values differ by >= 2^-48 relative, which survives the
+//   rounding of the quotients, so  x<y  <=>  rx*wy < ry*wx  exactly.
+//   1-x<y is decided by the same products when |x+y-1| is clearly non-zero; inside a 2^-40 band the
+//   reference's own divisions are replayed.
+CPAB_HD_NOINLINE int triangle_2d_exact(float rx, float ry, float wx, float wy)
+{
+    const double a = (double)rx * (double)wy;               // exact
+    const double b = (double)ry * (double)wx;               // exact
+    const double P = (double)wx * (double)wy;               // exact
+    const bool x_lt_y = a < b;
+    const double S = a + b;
+    bool anti;                                              // 1 - x < y
+    const double band = P * 9.094947017729282e-13;          // 2^-40
+    if (S > P + band) anti = true;
+    else if (S < P - band) anti = false;
+    else {
+        const double lx = (double)rx / (double)wx, ly = (double)ry / (double)wy;
+        anti = (1 - lx) < ly;
+    }
+    return x_lt_y ? (anti ? 2 : 3) : (anti ? 1 : 0);
+}
+
+CPAB_HD int find_cell_2d(float p0, float p1, const Geom& g)
+{
+    const bool lox = p0 <= 0.0f, hix = p0 >= g.span[0];
+    const bool loy = p1 <= 0.0f, hiy = p1 >= g.span[1];
+    // corner regions outside the domain need the reference's quotient comparisons
+    if ((lox | hix) & (loy | hiy)) return find_cell_2d_replay<float>(p0, p1, g);
+
+    float kx, rx, ky, ry;
+    divmod_exact(fmaxf(p0, 0.0f), g.nf[0], g.w[0], kx, rx);
+    divmod_exact(fmaxf(p1, 0.0f), g.nf[1], g.w[1], ky, ry);
+    kx = hix ? g.khi[0] : fminf(kx, g.nf[0] - 1.0f);
+    ky = hiy ? g.khi[1] : fminf(ky, g.nf[1] - 1.0f);
+
+    // approximate local coordinates (|error| < 3e-7) and the two diagonal tests
+    const float xf = rx * g.nf[0], yf = ry * g.nf[1];
+    const float d1 = xf - yf;                               // < 0  <=>  x < y
+    const float d2 = (1.0f - xf) - yf;                      // < 0  <=>  1 - x < y
+    int tri = (d1 < 0.0f) ? ((d2 < 0.0f) ? 2 : 3) : ((d2 < 0.0f) ? 1 : 0);
+    const bool inside = !(lox | hix | loy | hiy);
+    if (inside & (fminf(fabsf(d1), fabsf(d2)) < 2e-6f))
+        tri = triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
+    // outside one axis only: the reference's priority is left, right, above, below
+    tri = hiy ? 2 : tri;
+    tri = loy ? 0 : tri;
+    tri = hix ? 1 : tri;
+    tri = lox ? 3 : tri;
+    return 4 * (int)fmaf(ky, g.nf[0], kx) + tri;
+}
+
+CPAB_HD int find_cell_2d(double p0, double p1, const Geom& g)
+{
+    return find_cell_2d_replay<double>(p0, p1, g);
+}
+
+// ------------------------------------------------------------------------------------------- 3-D
+// The reference's outside-the-box push (cpab_ops.cpp:119-137); all float/double ops as written.
+template <typename T>
+CPAB_HD void push_inside_3d(T& q0, T& q1, T& q2, T w0, T w1, T w2)
+{
+    const T half = (T)0.5;
+    q0 -= half; q1 -= half; q2 -= half;
+    const T ax = abs_t(q0), ay = abs_t(q1), az = abs_t(q2);
+    const T shx = (ax < ay && ax < az) ? half * w0 : (T)0;
+    const T shy = (ay < ax && ax < az) ? half * w1 : (T)0;
+    const T shz = (az < ax && ax < ay) ? half * w2 : (T)0;
+    if (ax > half) q0 = sign_t(half - shx, q0);
+    if (ay > half) q1 = sign_t(half - shy, q1);
+    if (az > half) q2 = sign_t(half - shz, q2);
+    q0 += half; q1 += half; q2 += half;
+}
+
+// Literal replay of cpab_ops.cpp:138-184 from the (already pushed) point; T = float or double.
+template <typename T>
+CPAB_HD_NOINLINE int find_cell_3d_replay(T q0, T q1, T q2, const Geom& g)
+{
+    const bool f32 = sizeof(T) == 4;
+    const T w0 = f32 ? (T)g.w[0] : (T)g.wd[0];
+    const T w1 = f32 ? (T)g.w[1] : (T)g.wd[1];
+    const T w2 = f32 ? (T)g.w[2] : (T)g.wd[2];
+    const T h0 = f32 ? (T)g.hi3[0] : (T)g.hi3d[0];
+    const T h1 = f32 ? (T)g.hi3[1] : (T)g.hi3d[1];
+    const T h2 = f32 ? (T)g.hi3[2] : (T)g.hi3d[2];
+    const T zero = (T)0;
+    T c0 = q0 > zero ? q0 : zero; if (h0 < c0) c0 = h0;
+    T c1 = q1 > zero ? q1 : zero; if (h1 < c1) c1 = h1;
+    T c2 = q2 > zero ? q2 : zero; if (h2 < c2) c2 = h2;
+    const double r0 = fmod((double)c0, (double)w0);
+    const double r1 = fmod((double)c1, (double)w1);
+    const double r2 = fmod((double)c2, (double)w2);
+    const int i = pick_min(g.nc[0] - 1, ((double)c0 - r0) / (double)w0);
+    const int j = pick_min(g.nc[1] - 1, ((double)c1 - r1) / (double)w1);
+    const int k = pick_min(g.nc[2] - 1, ((double)c2 - r2) / (double)w2);
+    int cell = 5 * (i + j * g.nc[0] + k * g.nc[0] * g.nc[1]);
+    double x = r0 / (double)w0, y = r1 / (double)w1, z = r2 / (double)w2;
+    if ((i + j + k) & 1) { const double t = x; x = y; y = 1 - t; }
+    if (-x - y + z >= 0) cell += 1;
+    else if (x + y + z - 2 >= 0) cell += 2;
+    else if (-x + y - z >= 0) cell += 3;
+    else if (x - y - z >= 0) cell += 4;
+    return cell;
+}
+
+CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g)
+{
+    float q0 = p0, q1 = p1, q2 = p2;
+    if (q0 < 0.0f || q0 > 1.0f || q1 < 0.0f || q1 > 1.0f)       // sic: z is not tested (:119)
+        push_inside_3d<float>(q0, q1, q2, g.w[0], g.w[1], g.w[2]);
+    const float c0 = fminf(g.hi3[0], fmaxf(0.0f, q0));
+    const float c1 = fminf(g.hi3[1], fmaxf(0.0f, q1));
+    const float c2 = fminf(g.hi3[2], fmaxf(0.0f, q2));
+    float kx, ky, kz, rx, ry, rz;
+    divmod_exact(c0, g.nf[0], g.w[0], kx, rx);
+    divmod_exact(c1, g.nf[1], g.w[1], ky, ry);
+    divmod_exact(c2, g.nf[2], g.w[2], kz, rz);
+    const int i = (int)fminf(kx, g.nf[0] - 1.0f);
+    const int j = (int)fminf(ky, g.nf[1] - 1.0f);
+    const int k = (int)fminf(kz, g.nf[2] - 1.0f);
+    float x = rx * g.nf[0], y = ry * g.nf[1];
+    const float z = rz * g.nf[2];
+    if ((i + j + k) & 1) { const float t = x; x = y; y = 1.0f - t; }
+    const float t1 = z - x - y, t2 = x + y + z - 2.0f, t3 = y - x - z, t4 = x - y - z;
+    const float nearest = fminf(fminf(fabsf(t1), fabsf(t2)), fminf(fabsf(t3), fabsf(t4)));
+    if (nearest < 4e-6f) return find_cell_3d_replay<float>(q0, q1, q2, g);
+    const int tet = (t1 >= 0.0f) ? 1 : (t2 >= 0.0f) ? 2 : (t3 >= 0.0f) ? 3 : (t4 >= 0.0f) ? 4 : 0;
+    return 5 * (i + g.nc[0] * (j + g.nc[1] * k)) + tet;
+}
+
+CPAB_HD int find_cell_3d(double p0, double p1, double p2, const Geom& g)
+{
+    double q0 = p0, q1 = p1, q2 = p2;
+    if (q0 < 0.0 || q0 > 1.0 || q1 < 0.0 || q1 > 1.0)
+        push_inside_3d<double>(q0, q1, q2, g.wd[0], g.wd[1], g.wd[2]);
+    return find_cell_3d_replay<double>(q0, q1, q2, g);
+}
+
+// ------------------------------------------------------------------------------- generic front end
+template <int NDIM, typename T>
+CPAB_HD int find_cell(const T* p, const Geom& g)
+{
+    if (NDIM == 1) return find_cell_1d(p[0], g);
+    if (NDIM == 2) return find_cell_2d(p[0], p[1], g);
+    return find_cell_3d(p[0], p[1], p[2], g);
+}
+
+}  // namespace cpab

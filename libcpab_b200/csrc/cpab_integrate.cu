@@ -1,0 +1,644 @@
+// cpab_integrate.cu -- integration of the CPA velocity field and its theta-gradient (sm_100a).
+//
+// Kernels in this file and the reference code each one replaces (paths under /root/reference):
+//
+//   k_findcellidx     libcpab/core/cpab_ops.cu:14-227 (device findcellidx) -- exposed for tests and
+//                     for Cpab.visualize_tesselation-style callers
+//   k_forward         libcpab/core/cpab_ops.cu:268-388 + launch libcpab/pytorch/transformer_cuda.cu:18-64
+//                     nstepsolver x { cell search ; p <- Trels[cell] [p;1] }
+//   k_jacobian        libcpab/core/cpab_ops.cu:390-697 + launch transformer_cuda.cu:66-119
+//                     the reference-layout [d,n_theta,ndim,nP] RK2 Jacobian (kept for drop-in and
+//                     op-level parity; d-fold redundant by construction)
+//   k_backward        the same RK2 discretisation restated as an adjoint sweep: one pass per
+//                     (point,theta) instead of one per (point,theta,k); accumulates
+//                     G[theta][cell] and never materialises the Jacobian.  Together with
+//                     k_grad_epilogue (dtheta = G . B) it replaces cpab_ops.cu:390-697 AND the
+//                     contraction libcpab/pytorch/transformer.py:201.
+//
+// Design notes (B200): one thread owns one (point,theta) trajectory; a CTA works on one theta so
+// that theta's per-cell matrices are staged ONCE in shared memory (2-D [10,10]: 9.6 KB) and every
+// step's gather is a shared-memory read; grid = n_theta x point-chunks, linearised in x (n_theta
+// can exceed 65535).  Loads/stores of the planar [ndim,nP] point arrays are unit-stride per
+// coordinate.  The loop trip count is fixed (nstepsolver), so divergence is confined to the rare
+// exact paths of the cell search.
+#include <string_view>
+
+#include "cpab_common.cuh"
+
+namespace cpab {
+
+// ---- rounding-controlled scalar ops ---------------------------------------------------------------
+template <typename T> struct Num;
+template <> struct Num<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ float atomic_add(float* p, float v) { return atomicAdd(p, v); }
+};
+template <> struct Num<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    static __device__ __forceinline__ double atomic_add(double* p, double v) { return atomicAdd(p, v); }
+};
+
+// ---- per-cell matrix fetch (vectorised; the row-major [n][n+1] block is 8/16-byte aligned) --------
+template <int NDIM> __device__ __forceinline__ void load_affine(const float* M, float* a)
+{
+    if (NDIM == 3) {
+        const float4* v = reinterpret_cast<const float4*>(M);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const float4 t = v[i]; a[4*i] = t.x; a[4*i+1] = t.y; a[4*i+2] = t.z; a[4*i+3] = t.w; }
+    } else {
+        const float2* v = reinterpret_cast<const float2*>(M);
+#pragma unroll
+        for (int i = 0; i < Dim<NDIM>::kPpc / 2; ++i) { const float2 t = v[i]; a[2*i] = t.x; a[2*i+1] = t.y; }
+    }
+}
+template <int NDIM> __device__ __forceinline__ void load_affine(const double* M, double* a)
+{
+    const double2* v = reinterpret_cast<const double2*>(M);
+#pragma unroll
+    for (int i = 0; i < Dim<NDIM>::kPpc / 2; ++i) { const double2 t = v[i]; a[2*i] = t.x; a[2*i+1] = t.y; }
+}
+
+// out = A [v;1] in the reference's left-to-right order with every product and sum rounded
+// (cpab_ops.cpp:192-206) -- bit-identical to the CPU reference.
+template <int NDIM, typename T>
+__device__ __forceinline__ void affine_strict(const T* A, const T* v, T* out)
+{
+#pragma unroll
+    for (int r = 0; r < NDIM; ++r) {
+        T acc = Num<T>::mul(A[r * (NDIM + 1)], v[0]);
+#pragma unroll
+        for (int c = 1; c < NDIM; ++c) acc = Num<T>::add(acc, Num<T>::mul(A[r * (NDIM + 1) + c], v[c]));
+        out[r] = Num<T>::add(acc, A[r * (NDIM + 1) + NDIM]);
+    }
+}
+// same map as a nest of FMAs (fast-math mode, and everywhere inside the gradient)
+template <int NDIM, typename T>
+__device__ __forceinline__ void affine_fma(const T* A, const T* v, T* out)
+{
+#pragma unroll
+    for (int r = 0; r < NDIM; ++r) {
+        T acc = A[r * (NDIM + 1) + NDIM];
+#pragma unroll
+        for (int c = NDIM - 1; c >= 0; --c) acc = Num<T>::fma(A[r * (NDIM + 1) + c], v[c], acc);
+        out[r] = acc;
+    }
+}
+// linear part only, strict order (cpab_ops.cpp:208-222)
+template <int NDIM, typename T>
+__device__ __forceinline__ void linear_strict(const T* A, const T* v, T* out)
+{
+#pragma unroll
+    for (int r = 0; r < NDIM; ++r) {
+        T acc = Num<T>::mul(A[r * (NDIM + 1)], v[0]);
+#pragma unroll
+        for (int c = 1; c < NDIM; ++c) acc = Num<T>::add(acc, Num<T>::mul(A[r * (NDIM + 1) + c], v[c]));
+        out[r] = acc;
+    }
+}
+
+// stage one theta's [nC][ppc] block into shared memory with 16-byte copies
+template <typename T>
+__device__ __forceinline__ void stage_block(T* dst, const T* __restrict__ src, int count)
+{
+    const int vec = 16 / sizeof(T);
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (count % vec) == 0) {
+        const int4* s4 = reinterpret_cast<const int4*>(src);
+        int4* d4 = reinterpret_cast<int4*>(dst);
+        for (int i = threadIdx.x; i < count / vec; i += blockDim.x) d4[i] = __ldg(s4 + i);
+    } else {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+}
+
+// =====================================================================================================
+// findcellidx
+// =====================================================================================================
+template <typename T, int NDIM>
+__global__ void __launch_bounds__(256) k_findcellidx(const T* __restrict__ pts, long nP,
+                                                      int* __restrict__ out, const __grid_constant__ Geom g)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nP) return;
+    T p[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) p[j] = pts[i + (long)j * nP];
+    out[i] = find_cell<NDIM>(p, g);
+}
+
+// =====================================================================================================
+// forward: nsteps x { c = cell(p) ; p = Trels[theta][c] [p;1] }
+// =====================================================================================================
+template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT>
+__global__ void __launch_bounds__(256)
+k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restrict__ out, long nP,
+          int broadcast, int nsteps, const __grid_constant__ Geom g, int chunks, int chunk_pts)
+{
+    constexpr int PPC = Dim<NDIM>::kPpc;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int theta = blockIdx.x / chunks;
+    const int chunk = blockIdx.x - theta * chunks;
+    const int tsize = g.n_cells * PPC;
+    const T* Tm = trels + (size_t)theta * tsize;
+    if (SMEM) {
+        T* sT = reinterpret_cast<T*>(smem_raw);
+        stage_block(sT, Tm, tsize);
+        __syncthreads();
+        Tm = sT;
+    }
+    const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
+    T* dst = out + (size_t)theta * NDIM * nP;
+    const long begin = (long)chunk * chunk_pts;
+    const long end = begin + chunk_pts < nP ? begin + chunk_pts : nP;
+
+    for (long base = begin + threadIdx.x; base < end; base += (long)blockDim.x * PPT) {
+        T p[PPT][NDIM];
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const long i = base + (long)u * blockDim.x;
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) p[u][j] = i < end ? src[i + (long)j * nP] : (T)0.25;
+        }
+        for (int s = 0; s < nsteps; ++s) {
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
+                const int c = find_cell<NDIM>(p[u], g);
+                T a[PPC], q[NDIM];
+                load_affine<NDIM>(Tm + c * PPC, a);
+                if (STRICT) affine_strict<NDIM>(a, p[u], q); else affine_fma<NDIM>(a, p[u], q);
+#pragma unroll
+                for (int j = 0; j < NDIM; ++j) p[u][j] = q[j];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const long i = base + (long)u * blockDim.x;
+            if (i < end) {
+#pragma unroll
+                for (int j = 0; j < NDIM; ++j) dst[i + (long)j * nP] = p[u][j];
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+// reference-layout Jacobian: per (point, theta, k), RK2 with the reference's `double h`
+// (cpab_ops.cpp:289-366).  Every float expression is evaluated in the reference's order.
+// =====================================================================================================
+template <typename T, int NDIM>
+__global__ void __launch_bounds__(128)
+k_jacobian(const T* __restrict__ points, const T* __restrict__ As, const T* __restrict__ Bs,
+           T* __restrict__ jac, long nP, int n_theta, int d, int broadcast, int nsteps, const __grid_constant__ Geom g)
+{
+    constexpr int PPC = Dim<NDIM>::kPpc;
+    const int tk = blockIdx.y;                      // theta * d + k  (host keeps n_theta*d <= 65535,
+    const int theta = tk / d, k = tk - theta * d;   //  otherwise loops over slabs)
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nP) return;
+    const size_t tsize = (size_t)g.n_cells * PPC;
+    const T* At = As + (size_t)theta * tsize;
+    const T* Bk = Bs + (size_t)k * tsize;
+    const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
+    const double h = 1.0 / nsteps;
+
+    T p[NDIM], q[NDIM];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) { p[j] = src[i + (long)j * nP]; q[j] = 0; }
+    for (int s = 0; s < nsteps; ++s) {
+        const int c = find_cell<NDIM>(p, g);
+        T A[PPC], B[PPC];
+        load_affine<NDIM>(At + (size_t)c * PPC, A);
+        load_affine<NDIM>(Bk + (size_t)c * PPC, B);
+        T v[NDIM], pm[NDIM], vm[NDIM], bt[NDIM], aq[NDIM], u[NDIM], qm[NDIM], um[NDIM];
+        affine_strict<NDIM>(A, p, v);
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j)   // p + h*v/2.0 in double, rounded on store
+            pm[j] = (T)__dadd_rn((double)p[j], __dmul_rn(__dmul_rn(h, (double)v[j]), 0.5));
+        affine_strict<NDIM>(A, pm, vm);
+        affine_strict<NDIM>(B, p, bt);
+        linear_strict<NDIM>(A, q, aq);
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) u[j] = Num<T>::add(bt[j], aq[j]);
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j)
+            qm[j] = (T)__dadd_rn((double)q[j], __dmul_rn(__dmul_rn(h, (double)u[j]), 0.5));
+        affine_strict<NDIM>(B, pm, bt);
+        linear_strict<NDIM>(A, qm, aq);
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) um[j] = Num<T>::add(bt[j], aq[j]);
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) q[j] = (T)__dadd_rn((double)q[j], __dmul_rn((double)um[j], h));
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) p[j] = (T)__dadd_rn((double)p[j], __dmul_rn((double)vm[j], h));
+    }
+    T* dst = jac + ((size_t)k * n_theta + theta) * NDIM * nP;
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) dst[i + (long)j * nP] = q[j];
+}
+
+// =====================================================================================================
+// adjoint backward.
+//
+// Per step (cell c, A = A_c, h = 1/nsteps) the reference's RK2 recursion for the sensitivity
+// q_k = dp/dtheta_k is   q+ = M q + h B_kc [pMid;1] + (h^2/2) A_lin B_kc [p;1],
+// M = I + h A_lin + (h^2/2) A_lin^2, which is linear in the entries of B_k restricted to cell c.
+// With lambda_N = dL/dp_N and lambda_n = M_n^T lambda_{n+1},
+//     dL/dtheta_k = sum_c < B_kc , G_c >,   G_c += h lambda_{n+1} [pMid;1]^T + (h^2/2)(A_lin^T lambda_{n+1}) [p;1]^T
+// so one reverse sweep per (point,theta) yields G[theta] (nC x ndim x (ndim+1)) and the epilogue
+// dtheta = G . B finishes the job; lambda_0 is dL/dpoints for free.
+//
+// The reverse sweep needs p_n.  Trajectories are checkpointed every SEG steps in shared memory
+// during a first forward pass and recomputed segment by segment into registers.
+// =====================================================================================================
+template <int NDIM, typename T>
+__device__ __forceinline__ void rk2_step(const T* A, T* p, T h, T hh)
+{
+    T v[NDIM], pm[NDIM], vm[NDIM];
+    affine_fma<NDIM>(A, p, v);
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) pm[j] = Num<T>::fma(hh, v[j], p[j]);
+    affine_fma<NDIM>(A, pm, vm);
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) p[j] = Num<T>::fma(h, vm[j], p[j]);
+}
+
+template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __restrict__ gout,
+           T* __restrict__ G, T* __restrict__ dpoints, long nP, int broadcast, int nsteps, const __grid_constant__ Geom g,
+           int chunks, int chunk_pts)
+{
+    constexpr int PPC = Dim<NDIM>::kPpc;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int theta = blockIdx.x / chunks;
+    const int chunk = blockIdx.x - theta * chunks;
+    const int tsize = g.n_cells * PPC;
+    const int nseg = (nsteps + SEG - 1) / SEG;
+
+    // shared layout: [A block][G block] (if SMEM) then checkpoints [nseg][NDIM][BLOCK]
+    T* sA = reinterpret_cast<T*>(smem_raw);
+    T* sG = sA + (SMEM ? tsize : 0);
+    T* ck = sG + (SMEM ? tsize : 0);
+    const T* Am = As + (size_t)theta * tsize;
+    T* Gm = G + (size_t)theta * tsize;
+    if (SMEM) {
+        stage_block(sA, Am, tsize);
+        for (int i = threadIdx.x; i < tsize; i += BLOCK) sG[i] = 0;
+        __syncthreads();
+        Am = sA;
+        Gm = sG;
+    }
+    const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
+    const T* gsrc = gout + (size_t)theta * NDIM * nP;
+    const long begin = (long)chunk * chunk_pts;
+    const long end = begin + chunk_pts < nP ? begin + chunk_pts : nP;
+    const T h = (T)(1.0 / nsteps), hh = (T)(0.5 / nsteps), h2 = (T)(0.5 / nsteps / nsteps);
+
+    for (long i = begin + threadIdx.x; i < end; i += BLOCK) {
+        T p[NDIM], lam[NDIM];
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) { p[j] = src[i + (long)j * nP]; lam[j] = gsrc[i + (long)j * nP]; }
+
+        // ---- pass 1: checkpoints at the start of every segment (the last segment is not run)
+        for (int sg = 0; sg < nseg; ++sg) {
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) ck[(sg * NDIM + j) * BLOCK + threadIdx.x] = p[j];
+            if (sg + 1 < nseg) {
+#pragma unroll
+                for (int s = 0; s < SEG; ++s) {
+                    T a[PPC];
+                    load_affine<NDIM>(Am + find_cell<NDIM>(p, g) * PPC, a);
+                    rk2_step<NDIM>(a, p, h, hh);
+                }
+            }
+        }
+
+        // ---- pass 2: segments in reverse; recompute into registers, then sweep lambda back
+        T acc[PPC];
+        int cur = -1;
+#pragma unroll
+        for (int e = 0; e < PPC; ++e) acc[e] = 0;
+        for (int sg = nseg - 1; sg >= 0; --sg) {
+            const int len = (nsteps - sg * SEG) < SEG ? (nsteps - sg * SEG) : SEG;
+            T ps[SEG][NDIM];
+            int cs[SEG];
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) p[j] = ck[(sg * NDIM + j) * BLOCK + threadIdx.x];
+#pragma unroll
+            for (int s = 0; s < SEG; ++s) {
+                if (s < len) {
+#pragma unroll
+                    for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
+                    cs[s] = find_cell<NDIM>(p, g);
+                    if (s + 1 < len) {
+                        T a[PPC];
+                        load_affine<NDIM>(Am + cs[s] * PPC, a);
+                        rk2_step<NDIM>(a, p, h, hh);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = SEG - 1; s >= 0; --s) {
+                if (s < len) {
+                    const int c = cs[s];
+                    T a[PPC], v[NDIM], pm[NDIM], w[NDIM];
+                    load_affine<NDIM>(Am + c * PPC, a);
+                    affine_fma<NDIM>(a, ps[s], v);
+#pragma unroll
+                    for (int j = 0; j < NDIM; ++j) pm[j] = Num<T>::fma(hh, v[j], ps[s][j]);
+                    // w = A_lin^T lambda
+#pragma unroll
+                    for (int r = 0; r < NDIM; ++r) {
+                        T t = 0;
+#pragma unroll
+                        for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], lam[j], t);
+                        w[r] = t;
+                    }
+                    if (c != cur) {
+                        if (cur >= 0) {
+#pragma unroll
+                            for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gm + cur * PPC + e, acc[e]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < PPC; ++e) acc[e] = 0;
+                        cur = c;
+                    }
+#pragma unroll
+                    for (int r = 0; r < NDIM; ++r) {
+                        const T hl = h * lam[r], hw = h2 * w[r];
+#pragma unroll
+                        for (int cc = 0; cc < NDIM; ++cc)
+                            acc[r * (NDIM + 1) + cc] += Num<T>::fma(hl, pm[cc], hw * ps[s][cc]);
+                        acc[r * (NDIM + 1) + NDIM] += hl + hw;
+                    }
+                    // lambda <- lambda + h w + (h^2/2) A_lin^T w
+#pragma unroll
+                    for (int r = 0; r < NDIM; ++r) {
+                        T t = 0;
+#pragma unroll
+                        for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], w[j], t);
+                        lam[r] = Num<T>::fma(h2, t, Num<T>::fma(h, w[r], lam[r]));
+                    }
+                }
+            }
+        }
+        if (cur >= 0) {
+#pragma unroll
+            for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gm + cur * PPC + e, acc[e]);
+        }
+        if (dpoints != nullptr) {
+            T* dp = dpoints + (size_t)theta * NDIM * nP;
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) dp[i + (long)j * nP] = lam[j];
+        }
+    }
+    if (SMEM) {
+        __syncthreads();
+        T* Gg = G + (size_t)theta * tsize;
+        for (int e = threadIdx.x; e < tsize; e += BLOCK) {
+            const T val = sG[e];
+            if (val != (T)0) Num<T>::atomic_add(Gg + e, val);
+        }
+    }
+}
+
+// dtheta[t][k] = sum_e G[t][e] * B[e][k]      (G [n_theta,D], B [D,d] row-major, dtheta [n_theta,d])
+template <typename T, int TT>
+__global__ void __launch_bounds__(128)
+k_grad_epilogue(const T* __restrict__ G, const T* __restrict__ B, T* __restrict__ dtheta,
+                int n_theta, int D, int d)
+{
+    constexpr int TILE = 256;
+    __shared__ T sG[TT][TILE];
+    const int t0 = blockIdx.x * TT;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    T acc[TT];
+#pragma unroll
+    for (int u = 0; u < TT; ++u) acc[u] = 0;
+    for (int e0 = 0; e0 < D; e0 += TILE) {
+        const int n = D - e0 < TILE ? D - e0 : TILE;
+        __syncthreads();
+        for (int x = threadIdx.x; x < TT * TILE; x += blockDim.x) {
+            const int u = x / TILE, e = x - u * TILE;
+            sG[u][e] = (t0 + u < n_theta && e < n) ? G[(size_t)(t0 + u) * D + e0 + e] : (T)0;
+        }
+        __syncthreads();
+        if (k < d) {
+            for (int e = 0; e < n; ++e) {
+                const T b = __ldg(B + (size_t)(e0 + e) * d + k);
+#pragma unroll
+                for (int u = 0; u < TT; ++u) acc[u] = Num<T>::fma(sG[u][e], b, acc[u]);
+            }
+        }
+    }
+    if (k < d) {
+#pragma unroll
+        for (int u = 0; u < TT; ++u)
+            if (t0 + u < n_theta) dtheta[(size_t)(t0 + u) * d + k] = acc[u];
+    }
+}
+
+// =====================================================================================================
+// host launchers
+// =====================================================================================================
+static int g_tune_fwd_ppt = 1;        // points advanced concurrently per thread in k_forward
+static int g_tune_chunk_pts = 2048;   // points of one theta handled by one CTA
+static int g_tune_bwd_seg = 10;       // checkpoint spacing of k_backward
+static int g_tune_bwd_block = 128;
+
+int set_tuning(const char* key, int value)
+{
+    const std::string_view k(key);
+    if (k == "fwd_ppt" && (value == 1 || value == 2)) { g_tune_fwd_ppt = value; return kOk; }
+    if (k == "chunk_pts" && value >= 256 && value % 256 == 0) { g_tune_chunk_pts = value; return kOk; }
+    if (k == "bwd_seg" && (value == 5 || value == 10)) { g_tune_bwd_seg = value; return kOk; }
+    if (k == "bwd_block" && (value == 64 || value == 128 || value == 256)) { g_tune_bwd_block = value; return kOk; }
+    set_error("unknown tuning key/value %s=%d", key, value);
+    return kErrArgument;
+}
+
+template <typename T, int NDIM>
+static int findcellidx_t(const Geom& g, const void* points, long nP, int* out, cudaStream_t st)
+{
+    if (nP == 0) return kOk;
+    const unsigned blocks = (unsigned)((nP + 255) / 256);
+    k_findcellidx<T, NDIM><<<blocks, 256, 0, st>>>((const T*)points, nP, out, g);
+    CPAB_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+int launch_findcellidx(int dtype, const Geom& g, const void* points, long nP, int* out, cudaStream_t st)
+{
+#define GO(T) (g.ndim == 1 ? findcellidx_t<T, 1>(g, points, nP, out, st) : g.ndim == 2 ? findcellidx_t<T, 2>(g, points, nP, out, st) : findcellidx_t<T, 3>(g, points, nP, out, st))
+    return dtype == kF32 ? GO(float) : GO(double);
+#undef GO
+}
+
+static void pick_chunks(long nP, int& chunks, int& chunk_pts)
+{
+    chunk_pts = g_tune_chunk_pts;
+    if (nP < chunk_pts) chunk_pts = (int)((nP + 255) / 256 * 256);
+    chunks = (int)((nP + chunk_pts - 1) / chunk_pts);
+}
+
+template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT>
+static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int broadcast,
+                          const void* points, const void* trels, void* out, cudaStream_t st)
+{
+    int chunks, chunk_pts;
+    pick_chunks(nP, chunks, chunk_pts);
+    const size_t smem = SMEM ? (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T) : 0;
+    auto kern = k_forward<T, NDIM, STRICT, SMEM, PPT>;
+    if (smem > 48 * 1024)
+        CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long blocks = (long long)n_theta * chunks;
+    if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+    kern<<<(unsigned)blocks, 256, smem, st>>>((const T*)points, (const T*)trels, (T*)out, nP,
+                                              broadcast, nsteps, g, chunks, chunk_pts);
+    CPAB_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+template <typename T, int NDIM>
+static int forward_t(int flags, const Geom& g, int nsteps, int n_theta, long nP, int broadcast,
+                     const void* points, const void* trels, void* out, cudaStream_t st)
+{
+    const bool smem = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T) <= 160 * 1024;
+    const bool strict = !(flags & kFlagFastMath);
+    const int ppt = g_tune_fwd_ppt;
+#define ARGS g, nsteps, n_theta, nP, broadcast, points, trels, out, st
+    if (smem) {
+        if (strict) return ppt == 2 ? forward_launch<T, NDIM, true, true, 2>(ARGS) : forward_launch<T, NDIM, true, true, 1>(ARGS);
+        return ppt == 2 ? forward_launch<T, NDIM, false, true, 2>(ARGS) : forward_launch<T, NDIM, false, true, 1>(ARGS);
+    }
+    if (strict) return forward_launch<T, NDIM, true, false, 1>(ARGS);
+    return forward_launch<T, NDIM, false, false, 1>(ARGS);
+#undef ARGS
+}
+
+int launch_forward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, long nP,
+                   int broadcast, const void* points, const void* trels, void* out, cudaStream_t st)
+{
+    if (n_theta == 0 || nP == 0) return kOk;
+#define GO(T) (g.ndim == 1 ? forward_t<T, 1>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st) \
+             : g.ndim == 2 ? forward_t<T, 2>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st) \
+                           : forward_t<T, 3>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st))
+    return dtype == kF32 ? GO(float) : GO(double);
+#undef GO
+}
+
+template <typename T, int NDIM>
+static int jacobian_t(const Geom& g, int nsteps, int n_theta, int d, long nP, int broadcast,
+                      const void* points, const void* As, const void* Bs, void* jac, cudaStream_t st)
+{
+    const long long tk = (long long)n_theta * d;
+    if (tk > 65535) { set_error("jacobian: n_theta*d = %lld exceeds 65535 (use backward_theta)", tk); return kErrUnsupported; }
+    dim3 grid((unsigned)((nP + 127) / 128), (unsigned)tk);
+    k_jacobian<T, NDIM><<<grid, 128, 0, st>>>((const T*)points, (const T*)As, (const T*)Bs, (T*)jac,
+                                               nP, n_theta, d, broadcast, nsteps, g);
+    CPAB_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+int launch_jacobian(int dtype, const Geom& g, int nsteps, int n_theta, int d, long nP, int broadcast,
+                    const void* points, const void* As, const void* Bs, void* jac, cudaStream_t st)
+{
+    if (n_theta == 0 || nP == 0 || d == 0) return kOk;
+#define GO(T) (g.ndim == 1 ? jacobian_t<T, 1>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st) \
+             : g.ndim == 2 ? jacobian_t<T, 2>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st) \
+                           : jacobian_t<T, 3>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st))
+    return dtype == kF32 ? GO(float) : GO(double);
+#undef GO
+}
+
+size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta)
+{
+    const size_t elt = dtype == kF32 ? 4 : 8;
+    return (size_t)n_theta * g.n_cells * g.ndim * (g.ndim + 1) * elt;
+}
+
+template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
+static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int broadcast,
+                           const void* points, const void* As, const void* gout, void* G,
+                           void* dpoints, cudaStream_t st, bool& fits)
+{
+    int chunks, chunk_pts;
+    pick_chunks(nP, chunks, chunk_pts);
+    const int nseg = (nsteps + SEG - 1) / SEG;
+    const size_t tbytes = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
+    const size_t smem = (SMEM ? 2 * tbytes : 0) + (size_t)nseg * NDIM * BLOCK * sizeof(T);
+    fits = smem <= kMaxSmemBytes;
+    if (!fits) return kOk;
+    auto kern = k_backward<T, NDIM, SEG, SMEM, BLOCK>;
+    if (smem > 48 * 1024)
+        CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long blocks = (long long)n_theta * chunks;
+    if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+    kern<<<(unsigned)blocks, BLOCK, smem, st>>>((const T*)points, (const T*)As, (const T*)gout, (T*)G,
+                                                (T*)dpoints, nP, broadcast, nsteps, g, chunks, chunk_pts);
+    CPAB_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+template <typename T, int NDIM>
+static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, int broadcast,
+                      const void* points, const void* As, const void* basis, const void* gout,
+                      void* dtheta, void* dpoints, void* ws, cudaStream_t st)
+{
+    const int D = g.n_cells * Dim<NDIM>::kPpc;
+    CPAB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)n_theta * D * sizeof(T), st));
+    bool fits = false;
+    int rc = kOk;
+#define TRY(SEG, SMEM, BLOCK)                                                                      \
+    if (!fits && rc == kOk)                                                                        \
+        rc = backward_launch<T, NDIM, SEG, SMEM, BLOCK>(g, nsteps, n_theta, nP, broadcast, points, \
+                                                        As, gout, ws, dpoints, st, fits)
+    // preferred configuration first, then progressively smaller shared-memory footprints
+    if (g_tune_bwd_seg == 5) {
+        if (g_tune_bwd_block == 256) TRY(5, true, 256);
+        if (g_tune_bwd_block == 64) TRY(5, true, 64);
+        TRY(5, true, 128);
+    } else {
+        if (g_tune_bwd_block == 256) TRY(10, true, 256);
+        if (g_tune_bwd_block == 64) TRY(10, true, 64);
+        TRY(10, true, 128);
+    }
+    TRY(10, true, 64);
+    TRY(10, false, 128);
+    TRY(10, false, 64);
+#undef TRY
+    if (rc != kOk) return rc;
+    if (!fits) {
+        set_error("backward: nstepsolver=%d needs more checkpoint memory than one CTA has", nsteps);
+        return kErrUnsupported;
+    }
+    constexpr int TT = 8;
+    dim3 grid((unsigned)((n_theta + TT - 1) / TT), (unsigned)((d + 127) / 128));
+    k_grad_epilogue<T, TT><<<grid, 128, 0, st>>>((const T*)ws, (const T*)basis, (T*)dtheta, n_theta, D, d);
+    CPAB_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int d, long nP,
+                    int broadcast, const void* points, const void* As, const void* basis,
+                    const void* grad_out, void* dtheta, void* dpoints, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st)
+{
+    (void)flags;
+    if (n_theta == 0 || d == 0) return kOk;
+    if (workspace_bytes < backward_workspace_bytes(dtype, g, n_theta)) {
+        set_error("backward: workspace has %zu bytes, needs %zu", workspace_bytes,
+                  backward_workspace_bytes(dtype, g, n_theta));
+        return kErrWorkspace;
+    }
+#define GO(T) (g.ndim == 1 ? backward_t<T, 1>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st) \
+             : g.ndim == 2 ? backward_t<T, 2>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st) \
+                           : backward_t<T, 3>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st))
+    return dtype == kF32 ? GO(float) : GO(double);
+#undef GO
+}
+
+}  // namespace cpab

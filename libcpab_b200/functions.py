@@ -1,0 +1,128 @@
+"""Backend module with the names libcpab.cpab.Cpab calls on `self.backend`
+(libcpab/pytorch/functions.py).  Everything here is host-side torch plumbing except
+`transformer`, `interpolate` and `findcellidx`, which go to the CUDA library.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .interpolation import interpolate            # noqa: F401  (part of the backend interface)
+from .transformer import CPAB_transformer as transformer   # noqa: F401
+
+
+def assert_version():
+    major, minor = (int(v) for v in torch.__version__.split(".")[:2])
+    assert (major, minor) >= (1, 0), "pytorch 1.0.0 or newer is required"
+
+
+def _device(device):
+    if isinstance(device, torch.device):
+        return device
+    if device is None:
+        return None
+    return torch.device("cuda") if device in ("gpu", "cuda") else torch.device(device)
+
+
+def to(x, dtype=torch.float32, device=None):
+    if isinstance(x, torch.Tensor):
+        return x.to(dtype=dtype, device=_device(device))
+    return torch.tensor(x, dtype=dtype, device=_device(device))
+
+
+def tonumpy(x):
+    return x.detach().cpu().numpy()
+
+
+def check_device(x, device_name):
+    return x.is_cuda == (device_name == "gpu")
+
+
+def backend_type():
+    return torch.Tensor
+
+
+def pdist(mat):
+    norm = torch.sum(mat * mat, 1).reshape(-1, 1)
+    return norm - 2 * mat.mm(mat.t()) + norm.t()
+
+
+def norm(x):
+    return torch.norm(x)
+
+
+def matmul(x, y):
+    return torch.matmul(x, y)
+
+
+def transpose(x):
+    return x.t()
+
+
+def exp(x):
+    return torch.exp(x)
+
+
+def zeros(*s, device=None):
+    return torch.zeros(*s, device=_device(device))
+
+
+def ones(*s, device=None):
+    return torch.ones(*s, device=_device(device))
+
+
+def arange(x):
+    return torch.arange(x)
+
+
+def repeat(x, reps):
+    return x.repeat(reps)
+
+
+def batch_repeat(x, reps):
+    return x.repeat(reps, *(x.dim() * [1]))
+
+
+def maximum(x):
+    return x.max()
+
+
+def sample_transformation(d, n_sample=1, mean=None, cov=None, device="cpu"):
+    dev = _device(device)
+    mean = torch.zeros(d, dtype=torch.float32, device=dev) if mean is None else mean
+    cov = torch.eye(d, dtype=torch.float32, device=dev) if cov is None else cov
+    dist = torch.distributions.MultivariateNormal(mean, cov)
+    return dist.sample((n_sample,)).to(dev)
+
+
+def identity(d, n_sample=1, epsilon=0, device="cpu"):
+    assert epsilon >= 0, "epsilon need to be larger than 0"
+    return torch.zeros(n_sample, d, dtype=torch.float32, device=_device(device)) + epsilon
+
+
+def uniform_meshgrid(ndim, domain_min, domain_max, n_points, device="cpu"):
+    """[ndim, nP] grid, first coordinate fastest (libcpab/pytorch/functions.py:102-108).
+
+    The 1-D linspaces are evaluated on the host and uploaded (a few KB): torch's CPU and CUDA
+    linspace kernels differ in the last bit, and a CPU-generated grid keeps the input
+    bit-identical to what the reference's CPU path integrates.
+    """
+    lin = [torch.linspace(domain_min[i], domain_max[i], n_points[i]).to(_device(device))
+           for i in range(ndim)]
+    mesh = torch.meshgrid(lin[::-1], indexing="ij")
+    return torch.cat([g.reshape(1, -1) for g in mesh[::-1]], dim=0)
+
+
+def findcellidx(ndim, grid, nc):
+    """Cell index of every grid point, int32 [nP] -- the integrators' own (C++-exact) search."""
+    assert grid.shape[0] == ndim
+    return ops.findcellidx(grid, nc)
+
+
+def calc_vectorfield(grid, theta, params):
+    """Velocity at every grid point for one theta (libcpab/pytorch/functions.py:111-129)."""
+    B = to(params.basis, dtype=theta.dtype, device=theta.device)
+    As = torch.matmul(B, theta.flatten()).reshape(params.nC, *params.Ashape)
+    idx = findcellidx(params.ndim, grid, params.nc).long()
+    homog = torch.cat((grid, torch.ones(1, grid.shape[1], device=grid.device, dtype=grid.dtype)), 0)
+    return torch.einsum("pij,jp->ip", As[idx], homog)

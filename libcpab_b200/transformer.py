@@ -1,0 +1,81 @@
+"""`transformer(grid, theta, params)` -- the integrator behind Cpab.transform_grid.
+
+Mirrors the role of libcpab/pytorch/transformer.py (CPAB_transformer ->
+_CPABFunction_AnalyticGrad, :72-202) with the native calls replaced by the C ABI:
+
+    forward : theta --cpab_b200_theta_to_trels--> (As, Trels) --cpab_b200_forward--> points
+    backward: cpab_b200_backward_theta (adjoint sweep + G.B epilogue) -> dL/dtheta
+
+Differences a caller can observe, all deliberate:
+* the basis is uploaded to the device once per Cpab instance (the reference re-uploads it on
+  every call, transformer.py:146);
+* there is no slow path and no numeric-gradient path: `use_slow=True` / `numeric_grad=True`
+  raise instead of silently changing algorithm (north_star: no fallback);
+* the gradient w.r.t. `points` is None by default, exactly like the reference
+  (transformer.py:202), so CpabSequential trains only its last warp unless
+  `params.points_grad = True` is set, in which case the adjoint's lambda_0 is returned.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class _BasisCache:
+    """Device copies of B [D,d] and B^T [d,D] per (device, dtype), built lazily."""
+
+    def __init__(self, basis):
+        self._host = basis
+        self._dev = {}
+
+    def get(self, device, dtype):
+        key = (str(device), dtype)
+        if key not in self._dev:
+            b = torch.as_tensor(self._host, dtype=torch.float64).to(dtype).to(device).contiguous()
+            self._dev[key] = (b, b.t().contiguous())
+        return self._dev[key]
+
+
+def _basis(params, device, dtype):
+    cache = getattr(params, "_basis_cache", None)
+    if cache is None or cache._host is not params.basis:
+        cache = _BasisCache(params.basis)
+        params._basis_cache = cache
+    return cache.get(device, dtype)
+
+
+class _CpabFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, theta, params):
+        B, Bt = _basis(params, theta.device, theta.dtype)
+        As, trels = ops.theta_to_trels(theta, Bt, params.nc, params.nstepsolver)
+        newpoints = ops.forward(points, trels, params.nc, params.nstepsolver,
+                                fast_math=bool(getattr(params, "fast_math", False)))
+        ctx.save_for_backward(points, As, B)
+        ctx.params = params
+        ctx.points_need_grad = points.requires_grad and bool(getattr(params, "points_grad", False))
+        return newpoints
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        points, As, B = ctx.saved_tensors
+        p = ctx.params
+        dtheta, dpoints = ops.backward_theta(points, As, B, grad.contiguous(), p.nc, p.nstepsolver,
+                                             want_dpoints=ctx.points_need_grad)
+        if dpoints is not None and points.dim() == 2:
+            dpoints = dpoints.sum(dim=0)          # one grid shared by every theta
+        return dpoints, dtheta, None
+
+
+def CPAB_transformer(points, theta, params):
+    if getattr(params, "use_slow", False):
+        raise NotImplementedError("libcpab_b200 has no slow (pure python) integrator")
+    if getattr(params, "numeric_grad", False):
+        raise NotImplementedError("libcpab_b200 computes the analytic gradient only")
+    if not (points.is_cuda and theta.is_cuda):
+        raise RuntimeError("libcpab_b200 runs on CUDA tensors only (backend='pytorch', device='gpu')")
+    if points.dtype != theta.dtype:
+        raise TypeError("grid and theta must have the same dtype")
+    return _CpabFunction.apply(points, theta, params)

@@ -1,0 +1,54 @@
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def golden_cases():
+    """Names of the op/API-level fixtures generated from the reference (make_golden.py)."""
+    names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return [n for n in names if n not in ("cells", "expm", "seq_1d20x3")]
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def rel_err(x, ref):
+    """max|x-ref| / max|ref| -- the 'relative' of north_star's 1e-5."""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    den = np.abs(ref).max()
+    return float(np.abs(x - ref).max() / (den if den > 0 else 1.0))
+
+
+def bs_of(B, nc, dtype=np.float32):
+    """Reference's `Bs = B.t().view(d, nC, ndim, ndim+1)` (transformer.py:174)."""
+    ndim = len(nc)
+    nC = int({1: 1, 2: 4, 3: 5}[ndim] * np.prod(nc))
+    return np.ascontiguousarray(np.asarray(B).astype(dtype).T.reshape(B.shape[1], nC, ndim, ndim + 1))

@@ -1,0 +1,312 @@
+"""GPU parity of every C-ABI op against the oracle and the committed reference fixtures.
+
+Tolerances (north_star): cell indices bit-exact; points and gradients <= 1e-5 relative in
+float32 (relative = max|x-ref| / max|ref|), <= 1e-10 in the float64 check mode.  The strict
+(default) forward is held to the stronger bar it was designed for: bit-identical to the CPU
+reference for identical Trels.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bs_of, golden_cases, load_golden, rel_err
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-5
+F64_TOL = 1e-10
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ------------------------------------------------------------------------------------------ cells
+def test_findcellidx_golden_bit_exact():
+    from libcpab_b200 import ops
+    z = load_golden("cells")
+    for key in [k for k in z.files if k.startswith("pts_")]:
+        nc = [int(s) for s in key[4:].split("x")]
+        got = ops.findcellidx(dev(z[key]), nc).cpu().numpy()
+        assert np.array_equal(got, z["idx_" + key[4:]]), f"tessellation {nc}"
+
+
+@pytest.mark.parametrize("nc", [[1], [50], [100], [3, 3], [10, 10], [7, 4], [4, 4, 4], [3, 2, 5]])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_findcellidx_random_and_adversarial(nc, dtype):
+    from libcpab_b200 import ops
+    rng = np.random.default_rng(len(nc) * 100 + nc[0])
+    ndim, n = len(nc), 200_000
+    lat = np.stack([rng.integers(0, 4 * nc[j] + 1, n) / (4.0 * nc[j]) for j in range(ndim)])
+    latf = lat.astype(dtype)
+    edge = rng.integers(0, 2, (ndim, n)) + rng.choice([0, 1e-9, -1e-9, 1e-7, -1e-7, 0.05, -0.05], (ndim, n))
+    pts = np.concatenate([rng.uniform(-0.2, 1.2, (ndim, n)), rng.uniform(0, 1, (ndim, n)), lat,
+                          np.nextafter(latf, dtype(2)), np.nextafter(latf, dtype(-2)), edge],
+                         axis=1).astype(dtype)
+    got = ops.findcellidx(dev(pts), nc).cpu().numpy()
+    assert np.array_equal(got, O.findcellidx(pts, nc))
+
+
+# ------------------------------------------------------------------------------------------ expm
+def test_expm_matches_reference_pade13():
+    from libcpab_b200 import ops
+    z = load_golden("expm")
+    for m in (2, 3, 4):
+        got = ops.expm(dev(z[f"A{m}"])).cpu().numpy()
+        # the reference's own float32 Pade differs from its float64 Pade by a few ulp of the
+        # largest entry; ours is evaluated in double and rounded once
+        assert rel_err(got, z[f"E{m}_f64"]) < 2e-7
+        assert rel_err(got, z[f"E{m}"]) < 2e-5     # float32 reference incl. its squaring error
+        got64 = ops.expm(dev(z[f"A{m}"].astype(np.float64))).cpu().numpy()
+        assert rel_err(got64, z[f"E{m}_f64"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_theta_to_trels(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    nc = g["nc"].tolist()
+    Bt = dev(np.ascontiguousarray(g["B"].T), torch.float32)
+    As, Tr = ops.theta_to_trels(dev(g["theta"]), Bt, nc, int(g["nstepsolver"]))
+    assert rel_err(As.cpu().numpy(), g["As"]) < 1e-6
+    assert np.abs(Tr.cpu().numpy() - g["Trels"]).max() < 3e-7       # entries are O(1)
+    # float64 check mode against the numpy restatement
+    Bt64 = dev(np.ascontiguousarray(g["B"].T))
+    As64, Tr64 = ops.theta_to_trels(dev(g["theta"].astype(np.float64)), Bt64, nc, int(g["nstepsolver"]))
+    Ao = O.theta_to_affine(g["B"], g["theta"], nc, np.float64)
+    assert rel_err(As64.cpu().numpy(), Ao) < 1e-13
+    assert np.abs(Tr64.cpu().numpy() - O.affine_to_trels(Ao, int(g["nstepsolver"]))).max() < 1e-13
+
+
+# --------------------------------------------------------------------------------------- forward
+@pytest.mark.parametrize("name", golden_cases())
+def test_forward_strict_is_bit_identical_to_reference(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    nc = g["nc"].tolist()
+    got = ops.forward(dev(g["grid"]), dev(g["Trels"]), nc, int(g["nstepsolver"])).cpu().numpy()
+    assert np.array_equal(got, g["grid_t"]), "max diff %g" % np.abs(got - g["grid_t"]).max()
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_forward_fast_math_within_tolerance(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    got = ops.forward(dev(g["grid"]), dev(g["Trels"]), g["nc"].tolist(), int(g["nstepsolver"]),
+                      fast_math=True).cpu().numpy()
+    assert rel_err(got, g["grid_t"]) < F32_TOL
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_forward_fp64_check_mode(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    nc = g["nc"].tolist()
+    As = O.theta_to_affine(g["B"], g["theta"], nc, np.float64)
+    Tr = O.affine_to_trels(As, int(g["nstepsolver"]))
+    ref = O.forward(g["grid"].astype(np.float64), Tr, nc, int(g["nstepsolver"]))
+    got = ops.forward(dev(g["grid"].astype(np.float64)), dev(Tr), nc, int(g["nstepsolver"])).cpu().numpy()
+    assert rel_err(got, ref) < F64_TOL
+    if len(nc) < 3 or nc[0] == nc[2]:
+        # the reference's own numpy backend (scipy expm, float64); its 3-D cell search clamps z
+        # with inc_z where the C++ uses inc_x, so it only agrees on cubic tessellations
+        assert rel_err(got, g["grid_t_numpy64"]) < 1e-9
+
+
+def test_forward_broadcast_grid_and_trace():
+    """[n_theta,ndim,nP] grids (CpabSequential's 2nd+ warp) and per-step cell indices."""
+    from libcpab_b200 import ops
+    g = load_golden("d2_t3x3")
+    nc = g["nc"].tolist()
+    grids = np.ascontiguousarray(g["grid_t"])                 # one grid per theta
+    ref, cells = O.forward(grids, g["Trels"], nc, 50, trace=True)
+    got = ops.forward(dev(grids), dev(g["Trels"]), nc, 50).cpu().numpy()
+    assert np.array_equal(got, ref)
+    # the first step's cell indices, bit-exact
+    n_theta = grids.shape[0]
+    for t in range(n_theta):
+        idx = ops.findcellidx(dev(grids[t]), nc).cpu().numpy()
+        assert np.array_equal(idx, cells[t, 0])
+
+
+@pytest.mark.parametrize("nsteps", [1, 7, 50, 64])
+def test_forward_other_step_counts(nsteps):
+    from libcpab_b200 import ops
+    g = load_golden("d2_t3x3")
+    nc = g["nc"].tolist()
+    As = O.theta_to_affine(g["B"], g["theta"], nc)
+    Tr = O.affine_to_trels(As, nsteps)
+    got = ops.forward(dev(g["grid"]), dev(Tr), nc, nsteps).cpu().numpy()
+    assert np.array_equal(got, O.forward(g["grid"], Tr, nc, nsteps))
+
+
+def test_forward_ragged_sizes():
+    """nP not a multiple of anything, n_theta = 1, nP = 1, empty batches."""
+    from libcpab_b200 import ops
+    g = load_golden("d2_t3x3")
+    nc = g["nc"].tolist()
+    for nP in (1, 31, 257, 1023):
+        pts = np.ascontiguousarray(g["grid"][:, :nP])
+        got = ops.forward(dev(pts), dev(g["Trels"][:1]), nc, 50).cpu().numpy()
+        assert np.array_equal(got, O.forward(pts, g["Trels"][:1], nc, 50))
+    empty = ops.forward(dev(g["grid"][:, :0]), dev(g["Trels"]), nc, 50)
+    assert tuple(empty.shape) == (g["Trels"].shape[0], 2, 0)
+    none = ops.forward(dev(g["grid"]), dev(g["Trels"][:0]), nc, 50)
+    assert none.shape[0] == 0
+
+
+def test_forward_tuning_variants_are_equivalent():
+    from libcpab_b200 import _lib, ops
+    g = load_golden("d2_t10x10_vp")
+    nc = g["nc"].tolist()
+    base = ops.forward(dev(g["grid"]), dev(g["Trels"]), nc, 50).cpu().numpy()
+    try:
+        for key, val in (("fwd_ppt", 2), ("chunk_pts", 256), ("chunk_pts", 4096)):
+            _lib.set_tuning(key, val)
+            assert np.array_equal(ops.forward(dev(g["grid"]), dev(g["Trels"]), nc, 50).cpu().numpy(), base)
+    finally:
+        _lib.set_tuning("fwd_ppt", 1)
+        _lib.set_tuning("chunk_pts", 2048)
+
+
+# -------------------------------------------------------------------------------------- gradient
+@pytest.mark.parametrize("name", [n for n in golden_cases() if "jac" in load_golden(n).files])
+def test_jacobian_matches_reference_op(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    nc = g["nc"].tolist()
+    Bs = bs_of(g["B"], nc)
+    got = ops.backward_jacobian(dev(g["grid"]), dev(g["As"]), dev(Bs), nc, 50).cpu().numpy()
+    assert got.shape == g["jac"].shape
+    assert np.array_equal(got, g["jac"]), "max diff %g" % np.abs(got - g["jac"]).max()
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_backward_theta_matches_reference_gradient(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    nc = g["nc"].tolist()
+    dth, _ = ops.backward_theta(dev(g["grid"]), dev(g["As"]), dev(g["B"], torch.float32),
+                                dev(g["gout"]), nc, 50)
+    assert rel_err(dth.cpu().numpy(), g["dtheta"]) < F32_TOL
+
+
+@pytest.mark.parametrize("name", ["cfg1_1d50", "d2_t3x3", "d3_t2x2x2", "d2_t2x3_free_vp"])
+def test_backward_theta_fp64_check_mode(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    nc = g["nc"].tolist()
+    n_theta = min(2, g["theta"].shape[0])
+    As = O.theta_to_affine(g["B"], g["theta"][:n_theta], nc, np.float64)
+    grid = g["grid"].astype(np.float64)
+    gout = g["gout"][:n_theta].astype(np.float64)
+    ref = O.theta_grad(grid, As, bs_of(g["B"], nc, np.float64), gout, nc, 50, threads=8)
+    dth, _ = ops.backward_theta(dev(grid), dev(As), dev(g["B"]), dev(gout), nc, 50)
+    # the adjoint restates the same RK2 recursion; it differs from the per-k form only by
+    # floating-point association (and by `h` products the reference rounds through float)
+    assert rel_err(dth.cpu().numpy(), ref) < F64_TOL
+
+
+def test_backward_dpoints_against_differenced_flow():
+    """dL/dpoints (extension; the reference returns None) against central differences of the
+    oracle's float64 RK2 flow, on points whose trajectories stay clear of cell boundaries."""
+    from libcpab_b200 import ops
+    g = load_golden("d2_t3x3")
+    nc = g["nc"].tolist()
+    As = O.theta_to_affine(g["B"], g["theta"][:2], nc, np.float64) * 0.5
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0.02, 0.98, (2, 400))
+    gout = rng.normal(size=(2, 2, 400))
+    _, dp = ops.backward_theta(dev(pts), dev(As), dev(g["B"]), dev(gout), nc, 50, want_dpoints=True)
+    dp = dp.cpu().numpy()
+    eps = 1e-6
+    fd = np.zeros_like(dp)
+    for j in range(2):
+        e = np.zeros((2, 1)); e[j] = eps
+        fp, fm = O.rk2_flow(pts + e, As, nc), O.rk2_flow(pts - e, As, nc)
+        fd[:, j] = ((fp - fm) / (2 * eps) * gout).sum(axis=1)
+    # a trajectory that crosses a cell boundary has a kink the adjoint (like the reference's own
+    # gradient) ignores; compare where +-eps probes and the centre visit the same cells
+    _, c0 = O.forward(pts, O.affine_to_trels(As), nc, 50, trace=True)
+    same = (c0 == c0[:, :1]).all(axis=1)                    # never left the starting cell
+    assert same.mean() > 0.2
+    err = np.abs(dp - fd)[np.broadcast_to(same[:, None, :], dp.shape)]
+    assert err.max() < 1e-6 * max(1.0, np.abs(fd).max())
+
+
+def test_backward_other_step_counts_and_tuning():
+    from libcpab_b200 import _lib, ops
+    g = load_golden("d2_t3x3")
+    nc = g["nc"].tolist()
+    B32 = dev(g["B"], torch.float32)
+    for nsteps in (1, 7, 23, 50, 101):
+        ref = O.theta_grad(g["grid"], g["As"], bs_of(g["B"], nc), g["gout"], nc, nsteps, threads=8)
+        for seg, block in ((10, 128), (5, 64), (5, 256)):
+            try:
+                _lib.set_tuning("bwd_seg", seg)
+                _lib.set_tuning("bwd_block", block)
+                dth, _ = ops.backward_theta(dev(g["grid"]), dev(g["As"]), B32, dev(g["gout"]), nc, nsteps)
+            finally:
+                _lib.set_tuning("bwd_seg", 10)
+                _lib.set_tuning("bwd_block", 128)
+            assert rel_err(dth.cpu().numpy(), ref) < F32_TOL, (nsteps, seg, block)
+
+
+# --------------------------------------------------------------------------------- interpolation
+@pytest.mark.parametrize("name", [n for n in golden_cases() if "data" in load_golden(n).files])
+def test_interpolate_forward_bit_identical(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    out = ops.interpolate_forward(dev(g["data"]), dev(g["grid_t"]), g["grid_n"].tolist()).cpu().numpy()
+    assert out.shape == g["interp_out"].shape
+    assert np.array_equal(out, g["interp_out"]), "max diff %g" % np.abs(out - g["interp_out"]).max()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if "data" in load_golden(n).files])
+def test_interpolate_backward(name):
+    from libcpab_b200 import ops
+    g = load_golden(name)
+    dgrid, ddata = ops.interpolate_backward(dev(g["data"]), dev(g["grid_t"]), dev(g["data_gout"]),
+                                            want_dgrid=True, want_ddata=True)
+    assert rel_err(dgrid.cpu().numpy(), g["interp_dgrid"]) < F32_TOL
+    dg_o, dd_o = O.interpolate_vjp(g["data"], g["grid_t"], g["grid_n"].tolist(), g["data_gout"])
+    assert rel_err(ddata.cpu().numpy(), dd_o) < F32_TOL
+    assert rel_err(dgrid.cpu().numpy(), dg_o) < F32_TOL
+
+
+@pytest.mark.parametrize("shape,outsize", [((3, 2, 37), (53,)), ((2, 3, 19, 45), (33, 70)),
+                                           ((2, 2, 9, 11, 13), (17, 5, 40))])
+def test_interpolate_ragged_shapes_and_outside_points(shape, outsize):
+    from libcpab_b200 import ops
+    rng = np.random.default_rng(sum(shape))
+    ndim = len(shape) - 2
+    data = rng.uniform(size=shape).astype(np.float32)
+    grid = rng.uniform(-0.3, 1.3, (shape[0], ndim, int(np.prod(outsize)))).astype(np.float32)
+    out = ops.interpolate_forward(dev(data), dev(grid), outsize).cpu().numpy()
+    assert np.array_equal(out, O.interpolate(data, grid, outsize))
+    gout = rng.normal(size=out.shape).astype(np.float32)
+    dgrid, ddata = ops.interpolate_backward(dev(data), dev(grid), dev(gout), True, True)
+    dg_o, dd_o = O.interpolate_vjp(data, grid, outsize, gout)
+    assert rel_err(dgrid.cpu().numpy(), dg_o) < F32_TOL
+    assert rel_err(ddata.cpu().numpy(), dd_o) < F32_TOL
+    # float64 check mode
+    out64 = ops.interpolate_forward(dev(data.astype(np.float64)), dev(grid.astype(np.float64)), outsize)
+    assert rel_err(out64.cpu().numpy(), O.interpolate(data.astype(np.float64), grid.astype(np.float64), outsize)) < 1e-14
+
+
+# ------------------------------------------------------------------------------------- error path
+def test_errors_are_raised_not_swallowed():
+    from libcpab_b200 import _lib, ops
+    g = load_golden("d2_t3x3")
+    with pytest.raises(RuntimeError):
+        ops.forward(torch.from_numpy(g["grid"]), dev(g["Trels"]), [3, 3], 50)      # CPU tensor
+    with pytest.raises(ValueError):
+        ops.forward(dev(g["grid"]), dev(g["Trels"]), [4, 4], 50)                   # wrong tessellation
+    with pytest.raises(_lib.CpabError):
+        ops.forward(dev(g["grid"]), dev(g["Trels"]), [3, 3], 0)                    # nstepsolver = 0
+    with pytest.raises(_lib.CpabError):
+        _lib.set_tuning("no_such_knob", 1)
