@@ -59,6 +59,17 @@ const char* cpab_b200_build_info(void);
  * beyond floating-point summation order in the gradient. */
 int cpab_b200_set_tuning(const char* key, int value);
 
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+long long cpab_b200_launch_count(void);
+
+/* Per-kernel device timing.  enable(1) clears the accumulators and makes the library bracket its
+ * dominant kernels with CUDA events on the stream they are launched on; read() synchronises the
+ * recorded events and returns the accumulated milliseconds and launch count of one slot:
+ * 0 forward, 1 adjoint backward, 2 interpolate forward, 3 interpolate backward,
+ * 4 theta_to_trels, 5 gradient epilogue.  Off by default (no events are created). */
+int cpab_b200_profile_enable(int on);
+int cpab_b200_profile_read(int slot, double* total_ms, long long* launches);
+
 /* Diagnostic: `blocks` CTAs of 256 threads each run `iters` x 64 dependent-chain FP32 FMAs
  * (8 independent chains per thread).  bench.py times it to obtain the measured FP32 peak that
  * the integration roofline is quoted against.  `out` is one device float (never written). */

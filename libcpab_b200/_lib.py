@@ -28,6 +28,9 @@ SIGNATURES = {
     "cpab_b200_last_error": (ctypes.c_char_p, []),
     "cpab_b200_build_info": (ctypes.c_char_p, []),
     "cpab_b200_set_tuning": (_i, [ctypes.c_char_p, _i]),
+    "cpab_b200_launch_count": (ctypes.c_longlong, []),
+    "cpab_b200_profile_enable": (_i, [_i]),
+    "cpab_b200_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
     "cpab_b200_fp32_fma_probe": (_i, [_i, _i, _vp, _vp]),
     "cpab_b200_findcellidx": (_i, [_i, _i, _ip, _vp, _l, _vp, _vp]),
     "cpab_b200_theta_to_trels": (_i, [_i, _i, _ip, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -84,3 +87,23 @@ def nc_array(nc):
 
 def set_tuning(key: str, value: int) -> None:
     check(load().cpab_b200_set_tuning(key.encode(), int(value)), "set_tuning")
+
+
+PROFILE_SLOTS = {"forward": 0, "backward": 1, "interp_fwd": 2, "interp_bwd": 3,
+                 "theta_to_trels": 4, "epilogue": 5}
+
+
+def launch_count() -> int:
+    return int(load().cpab_b200_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(load().cpab_b200_profile_enable(1 if on else 0), "profile_enable")
+
+
+def profile_read(slot: str):
+    """(total_ms, launches) accumulated for one kernel slot since profile_enable(True)."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_longlong(0)
+    check(load().cpab_b200_profile_read(PROFILE_SLOTS[slot], ctypes.byref(ms), ctypes.byref(n)),
+          "profile_read")
+    return ms.value, n.value

@@ -3,7 +3,10 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/libcpab_b200.h"
 #include "cpab_common.cuh"
@@ -24,6 +27,52 @@ void set_error(const char* fmt, ...)
 const char* get_error() { return t_error.c_str(); }
 
 int set_tuning(const char* key, int value);   // cpab_integrate.cu
+
+// ---- instrumentation ---------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+struct ProfPair { cudaEvent_t a, b; int slot; };
+static std::vector<ProfPair> g_prof_pending;     // recorded, not yet read back
+static double g_prof_ms[kProfSlots];
+static long long g_prof_n[kProfSlots];
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool prof_begin(int slot, cudaStream_t st)
+{
+    if (!g_prof_on.load(std::memory_order_relaxed)) return false;
+    ProfPair p;
+    p.slot = slot;
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return false;
+    cudaEventRecord(p.a, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_pending.push_back(p);
+    return true;
+}
+
+void prof_end(int slot, cudaStream_t st)
+{
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto it = g_prof_pending.rbegin(); it != g_prof_pending.rend(); ++it)
+        if (it->slot == slot) { cudaEventRecord(it->b, st); return; }
+}
+
+static void prof_collect()
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& p : g_prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_prof_ms[p.slot] += ms;
+            g_prof_n[p.slot] += 1;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_prof_pending.clear();
+}
 
 static bool check_geom(int dtype, int ndim, const int* nc)
 {
@@ -64,6 +113,25 @@ int cpab_b200_set_tuning(const char* key, int value)
 {
     if (key == nullptr) { set_error("key is NULL"); return kErrArgument; }
     return set_tuning(key, value);
+}
+
+long long cpab_b200_launch_count(void) { return g_launches.load(); }
+
+int cpab_b200_profile_enable(int on)
+{
+    prof_collect();
+    for (int i = 0; i < kProfSlots; ++i) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
+    g_prof_on.store(on ? 1 : 0);
+    return kOk;
+}
+
+int cpab_b200_profile_read(int slot, double* total_ms, long long* launches)
+{
+    REQUIRE(slot >= 0 && slot < kProfSlots && total_ms && launches, "profile_read: bad arguments");
+    prof_collect();
+    *total_ms = g_prof_ms[slot];
+    *launches = g_prof_n[slot];
+    return kOk;
 }
 
 int cpab_b200_fp32_fma_probe(int blocks, int iters, void* out, void* stream)

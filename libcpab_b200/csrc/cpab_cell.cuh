@@ -43,6 +43,7 @@ struct Geom {
     int n_cells;        // simplices: nx | 4 nx ny | 5 nx ny nz
     // ---- float32 path -----------------------------------------------------------------------
     float nf[3];        // (float)n
+    float nm1[3];       // (float)(n-1)
     float w[3];         // cell width rounded to float: `const float inc = 1.0 / n`
     float span[3];      // (float)(n * inc): the upper domain bound the reference compares with
     float khi[3];       // 2-D: column/row (already min'ed with n-1) of a coordinate clamped high
@@ -72,6 +73,7 @@ inline Geom make_geom(int ndim, const int* nc)
         g.nc[j] = n;
         if (j < ndim) cells *= n;
         g.nf[j] = (float)n;
+        g.nm1[j] = (float)(n - 1);
         g.w[j] = (float)(1.0 / n);
         g.span[j] = (float)n * g.w[j];                       // int*float -> float multiply
         g.wd[j] = 1.0 / n;
@@ -91,16 +93,21 @@ inline Geom make_geom(int ndim, const int* nc)
 }
 
 // -------------------------------------------------------------------------------------------------
-// float32 building block: exact floor(p / w) and exact remainder for 0 <= p, p/w < 2^21.
+// float32 building block: exact floor(p / w) and exact remainder p - floor(p/w)*w for p >= 0.
+//
+// Requires n <= 2^20 (enforced by the ABI) and p/w < 2^21.  With n*w = 1 + delta, |delta| <= 2^-24,
+// the exact product p*n equals Q(1+delta) for the exact quotient Q = p/w, i.e. it is off by less
+// than 1/16; the FFMA against 1.5*2^23 rounds it to the nearest integer, so the estimate is
+// floor(Q) or floor(Q)+1 and never anything else.  r = fma(-k, w, p) is exact for both (a
+// multiple of ulp(w) of magnitude <= w), its sign tells which, and r + w is exact as well.
 // kf is returned as a float holding the integer.
 CPAB_HD void divmod_exact(float p, float nf, float w, float& kf, float& r)
 {
-    const float kMagic = 12582912.0f;                       // 1.5 * 2^23: adding it rounds to integer
-    const float t = fmaf(p, nf, kMagic);                    // RN(p*n) in the low mantissa bits
-    kf = t - kMagic;                                        // exact
-    r = fmaf(-kf, w, p);                                    // exact remainder for k in {k*, k*+1}
-    if (r < 0.0f) { kf -= 1.0f; r += w; }                   // estimate was one too high; r+w is exact
-    if (r >= w)   { kf += 1.0f; r = fmaf(-kf, w, p); }      // (only reachable through estimate error)
+    const float kMagic = 12582912.0f;                       // 1.5 * 2^23
+    const float t = fmaf(p, nf, kMagic);
+    kf = t - kMagic;
+    r = fmaf(-kf, w, p);
+    if (r < 0.0f) { kf -= 1.0f; r += w; }
 }
 
 // ------------------------------------------------------------------------------------------- 1-D
@@ -184,32 +191,33 @@ CPAB_HD_NOINLINE int triangle_2d_exact(float rx, float ry, float wx, float wy)
     return x_lt_y ? (anti ? 2 : 3) : (anti ? 1 : 0);
 }
 
+// Fast path.  A coordinate at or below 0 is clamped to 0 (column 0, local coordinate 0), one at
+// or above the span takes the host-evaluated column and local coordinate 1; with those
+// substitutions the in-domain diagonal tests reproduce the reference's out-of-bound branches
+// (left -> 3, right -> 1, above -> 0, below -> 2) whenever a single axis is outside, and every
+// corner region (both axes outside) lands exactly on a diagonal, i.e. in the guard band, from
+// where the reference's own expression sequence is replayed.
 CPAB_HD int find_cell_2d(float p0, float p1, const Geom& g)
 {
-    const bool lox = p0 <= 0.0f, hix = p0 >= g.span[0];
-    const bool loy = p1 <= 0.0f, hiy = p1 >= g.span[1];
-    // corner regions outside the domain need the reference's quotient comparisons
-    if ((lox | hix) & (loy | hiy)) return find_cell_2d_replay<float>(p0, p1, g);
-
     float kx, rx, ky, ry;
     divmod_exact(fmaxf(p0, 0.0f), g.nf[0], g.w[0], kx, rx);
     divmod_exact(fmaxf(p1, 0.0f), g.nf[1], g.w[1], ky, ry);
-    kx = hix ? g.khi[0] : fminf(kx, g.nf[0] - 1.0f);
-    ky = hiy ? g.khi[1] : fminf(ky, g.nf[1] - 1.0f);
-
+    const bool hix = p0 >= g.span[0], hiy = p1 >= g.span[1];
+    kx = hix ? g.khi[0] : fminf(kx, g.nm1[0]);
+    ky = hiy ? g.khi[1] : fminf(ky, g.nm1[1]);
     // approximate local coordinates (|error| < 3e-7) and the two diagonal tests
-    const float xf = rx * g.nf[0], yf = ry * g.nf[1];
+    const float xf = hix ? 1.0f : rx * g.nf[0];
+    const float yf = hiy ? 1.0f : ry * g.nf[1];
     const float d1 = xf - yf;                               // < 0  <=>  x < y
     const float d2 = (1.0f - xf) - yf;                      // < 0  <=>  1 - x < y
-    int tri = (d1 < 0.0f) ? ((d2 < 0.0f) ? 2 : 3) : ((d2 < 0.0f) ? 1 : 0);
-    const bool inside = !(lox | hix | loy | hiy);
-    if (inside & (fminf(fabsf(d1), fabsf(d2)) < 2e-6f))
+    int tri;
+    if (fminf(fabsf(d1), fabsf(d2)) < 2e-6f) {              // rare: on/near a diagonal or a corner
+        if (!(p0 > 0.0f) | hix | !(p1 > 0.0f) | hiy) return find_cell_2d_replay<float>(p0, p1, g);
         tri = triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
-    // outside one axis only: the reference's priority is left, right, above, below
-    tri = hiy ? 2 : tri;
-    tri = loy ? 0 : tri;
-    tri = hix ? 1 : tri;
-    tri = lox ? 3 : tri;
+    } else {
+        // (x<y, 1-x<y) -> (0,0):0 (0,1):1 (1,1):2 (1,0):3  ==  (x<y ? 3 : 0) ^ (1-x<y ? 1 : 0)
+        tri = (d1 < 0.0f ? 3 : 0) ^ (d2 < 0.0f ? 1 : 0);
+    }
     return 4 * (int)fmaf(ky, g.nf[0], kx) + tri;
 }
 
@@ -271,24 +279,24 @@ CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g)
     float q0 = p0, q1 = p1, q2 = p2;
     if (q0 < 0.0f || q0 > 1.0f || q1 < 0.0f || q1 > 1.0f)       // sic: z is not tested (:119)
         push_inside_3d<float>(q0, q1, q2, g.w[0], g.w[1], g.w[2]);
-    const float c0 = fminf(g.hi3[0], fmaxf(0.0f, q0));
-    const float c1 = fminf(g.hi3[1], fmaxf(0.0f, q1));
-    const float c2 = fminf(g.hi3[2], fmaxf(0.0f, q2));
     float kx, ky, kz, rx, ry, rz;
-    divmod_exact(c0, g.nf[0], g.w[0], kx, rx);
-    divmod_exact(c1, g.nf[1], g.w[1], ky, ry);
-    divmod_exact(c2, g.nf[2], g.w[2], kz, rz);
-    const int i = (int)fminf(kx, g.nf[0] - 1.0f);
-    const int j = (int)fminf(ky, g.nf[1] - 1.0f);
-    const int k = (int)fminf(kz, g.nf[2] - 1.0f);
+    divmod_exact(fminf(g.hi3[0], fmaxf(0.0f, q0)), g.nf[0], g.w[0], kx, rx);
+    divmod_exact(fminf(g.hi3[1], fmaxf(0.0f, q1)), g.nf[1], g.w[1], ky, ry);
+    divmod_exact(fminf(g.hi3[2], fmaxf(0.0f, q2)), g.nf[2], g.w[2], kz, rz);
+    kx = fminf(kx, g.nm1[0]);
+    ky = fminf(ky, g.nm1[1]);
+    kz = fminf(kz, g.nm1[2]);
+    const int cube = (int)fmaf(fmaf(kz, g.nf[1], ky), g.nf[0], kx);
+    const int par = (int)(kx + ky + kz);
     float x = rx * g.nf[0], y = ry * g.nf[1];
     const float z = rz * g.nf[2];
-    if ((i + j + k) & 1) { const float t = x; x = y; y = 1.0f - t; }
-    const float t1 = z - x - y, t2 = x + y + z - 2.0f, t3 = y - x - z, t4 = x - y - z;
+    if (par & 1) { const float t = x; x = y; y = 1.0f - t; }
+    const float s = x + y, u = y - x;
+    const float t1 = z - s, t2 = (s + z) - 2.0f, t3 = u - z, t4 = -u - z;
     const float nearest = fminf(fminf(fabsf(t1), fabsf(t2)), fminf(fabsf(t3), fabsf(t4)));
     if (nearest < 4e-6f) return find_cell_3d_replay<float>(q0, q1, q2, g);
     const int tet = (t1 >= 0.0f) ? 1 : (t2 >= 0.0f) ? 2 : (t3 >= 0.0f) ? 3 : (t4 >= 0.0f) ? 4 : 0;
-    return 5 * (i + g.nc[0] * (j + g.nc[1] * k)) + tet;
+    return 5 * cube + tet;
 }
 
 CPAB_HD int find_cell_3d(double p0, double p1, double p2, const Geom& g)

@@ -28,6 +28,17 @@ enum Flags : int {
 #define CPAB_STR(x) CPAB_STR2(x)
 
 void set_error(const char* fmt, ...);
+
+// ---- instrumentation (cpab_abi.cu) -----------------------------------------------------------------
+// Every kernel launch of this library goes through count_launch(); bench.py reports the total as
+// `gpu_launches`.  When profiling is switched on (cpab_b200_profile_enable), the dominant kernels
+// are bracketed by CUDA events on their own stream and the elapsed time is accumulated per slot.
+enum ProfSlot : int { kProfForward = 0, kProfBackward = 1, kProfInterpFwd = 2, kProfInterpBwd = 3,
+                      kProfThetaToTrels = 4, kProfEpilogue = 5, kProfSlots = 6 };
+void count_launch(int n = 1);
+bool prof_begin(int slot, cudaStream_t st);   // true if an event was recorded
+void prof_end(int slot, cudaStream_t st);
+
 int set_tuning(const char* key, int value);
 const char* get_error();
 

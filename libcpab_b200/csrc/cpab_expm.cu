@@ -228,8 +228,11 @@ int theta_to_trels_t(const Geom& g, int nsteps, int n_theta, int d, const void* 
     dim3 grid((unsigned)((g.n_cells + 127) / 128), (unsigned)n_theta);
     const size_t smem = (size_t)d * sizeof(T);
     if (smem > 48 * 1024) { set_error("theta dimension %d too large", d); return kErrUnsupported; }
+    prof_begin(kProfThetaToTrels, st);
     k_theta_to_trels<T, NDIM><<<grid, 128, smem, st>>>((const T*)basis_t, (const T*)theta, (T*)As,
                                                         (T*)trels, g.n_cells, d, nsteps);
+    prof_end(kProfThetaToTrels, st);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -238,6 +241,7 @@ template <typename T, int M>
 int expm_t(long n, const void* A, void* E, cudaStream_t st)
 {
     k_expm<T, M><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const T*)A, (T*)E, n);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }

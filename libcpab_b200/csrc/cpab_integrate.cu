@@ -268,8 +268,8 @@ __device__ __forceinline__ void rk2_step(const T* A, T* p, T h, T hh)
 template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __restrict__ gout,
-           T* __restrict__ G, T* __restrict__ dpoints, long nP, int broadcast, int nsteps, const __grid_constant__ Geom g,
-           int chunks, int chunk_pts)
+           T* __restrict__ G, T* __restrict__ dpoints, long nP, int broadcast, int nsteps,
+           const __grid_constant__ Geom g, int chunks, int chunk_pts)
 {
     constexpr int PPC = Dim<NDIM>::kPpc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -278,10 +278,14 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     const int tsize = g.n_cells * PPC;
     const int nseg = (nsteps + SEG - 1) / SEG;
 
-    // shared layout: [A block][G block] (if SMEM) then checkpoints [nseg][NDIM][BLOCK]
+    // shared layout: [A block][G block] (if SMEM), checkpoints [nseg][NDIM][BLOCK],
+    // cell trace [nsteps][BLOCK] (16-bit when the tessellation has < 65536 simplices)
     T* sA = reinterpret_cast<T*>(smem_raw);
     T* sG = sA + (SMEM ? tsize : 0);
     T* ck = sG + (SMEM ? tsize : 0);
+    unsigned short* ct16 = reinterpret_cast<unsigned short*>(ck + (size_t)nseg * NDIM * BLOCK);
+    int* ct32 = reinterpret_cast<int*>(ct16);
+    const bool wide = g.n_cells > 65535;
     const T* Am = As + (size_t)theta * tsize;
     T* Gm = G + (size_t)theta * tsize;
     if (SMEM) {
@@ -302,21 +306,28 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
 #pragma unroll
         for (int j = 0; j < NDIM; ++j) { p[j] = src[i + (long)j * nP]; lam[j] = gsrc[i + (long)j * nP]; }
 
-        // ---- pass 1: checkpoints at the start of every segment (the last segment is not run)
+        // ---- pass 1: the RK2 trajectory.  Records the cell of every step and a checkpoint of p
+        //      at the start of every segment; this is the only pass that searches cells.
         for (int sg = 0; sg < nseg; ++sg) {
 #pragma unroll
             for (int j = 0; j < NDIM; ++j) ck[(sg * NDIM + j) * BLOCK + threadIdx.x] = p[j];
-            if (sg + 1 < nseg) {
 #pragma unroll
-                for (int s = 0; s < SEG; ++s) {
-                    T a[PPC];
-                    load_affine<NDIM>(Am + find_cell<NDIM>(p, g) * PPC, a);
-                    rk2_step<NDIM>(a, p, h, hh);
+            for (int s = 0; s < SEG; ++s) {
+                const int n = sg * SEG + s;
+                if (n < nsteps) {
+                    const int c = find_cell<NDIM>(p, g);
+                    if (wide) ct32[n * BLOCK + threadIdx.x] = c;
+                    else ct16[n * BLOCK + threadIdx.x] = (unsigned short)c;
+                    if (n + 1 < nsteps) {
+                        T a[PPC];
+                        load_affine<NDIM>(Am + c * PPC, a);
+                        rk2_step<NDIM>(a, p, h, hh);
+                    }
                 }
             }
         }
 
-        // ---- pass 2: segments in reverse; recompute into registers, then sweep lambda back
+        // ---- pass 2: segments in reverse; replay p into registers (no search), sweep lambda back
         T acc[PPC];
         int cur = -1;
 #pragma unroll
@@ -330,9 +341,10 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
 #pragma unroll
             for (int s = 0; s < SEG; ++s) {
                 if (s < len) {
+                    const int n = sg * SEG + s;
+                    cs[s] = wide ? ct32[n * BLOCK + threadIdx.x] : (int)ct16[n * BLOCK + threadIdx.x];
 #pragma unroll
                     for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
-                    cs[s] = find_cell<NDIM>(p, g);
                     if (s + 1 < len) {
                         T a[PPC];
                         load_affine<NDIM>(Am + cs[s] * PPC, a);
@@ -446,7 +458,7 @@ k_grad_epilogue(const T* __restrict__ G, const T* __restrict__ B, T* __restrict_
 // =====================================================================================================
 static int g_tune_fwd_ppt = 1;        // points advanced concurrently per thread in k_forward
 static int g_tune_chunk_pts = 2048;   // points of one theta handled by one CTA
-static int g_tune_bwd_seg = 10;       // checkpoint spacing of k_backward
+static int g_tune_bwd_seg = 5;        // checkpoint spacing of k_backward
 static int g_tune_bwd_block = 128;
 
 int set_tuning(const char* key, int value)
@@ -466,6 +478,7 @@ static int findcellidx_t(const Geom& g, const void* points, long nP, int* out, c
     if (nP == 0) return kOk;
     const unsigned blocks = (unsigned)((nP + 255) / 256);
     k_findcellidx<T, NDIM><<<blocks, 256, 0, st>>>((const T*)points, nP, out, g);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -496,8 +509,11 @@ static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int b
         CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = (long long)n_theta * chunks;
     if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+    prof_begin(kProfForward, st);
     kern<<<(unsigned)blocks, 256, smem, st>>>((const T*)points, (const T*)trels, (T*)out, nP,
                                               broadcast, nsteps, g, chunks, chunk_pts);
+    prof_end(kProfForward, st);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -539,6 +555,7 @@ static int jacobian_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
     dim3 grid((unsigned)((nP + 127) / 128), (unsigned)tk);
     k_jacobian<T, NDIM><<<grid, 128, 0, st>>>((const T*)points, (const T*)As, (const T*)Bs, (T*)jac,
                                                nP, n_theta, d, broadcast, nsteps, g);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -569,7 +586,8 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
     pick_chunks(nP, chunks, chunk_pts);
     const int nseg = (nsteps + SEG - 1) / SEG;
     const size_t tbytes = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
-    const size_t smem = (SMEM ? 2 * tbytes : 0) + (size_t)nseg * NDIM * BLOCK * sizeof(T);
+    const size_t smem = (SMEM ? 2 * tbytes : 0) + (size_t)nseg * NDIM * BLOCK * sizeof(T) +
+                        (size_t)nsteps * BLOCK * (g.n_cells > 65535 ? 4 : 2);
     fits = smem <= kMaxSmemBytes;
     if (!fits) return kOk;
     auto kern = k_backward<T, NDIM, SEG, SMEM, BLOCK>;
@@ -577,8 +595,11 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
         CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = (long long)n_theta * chunks;
     if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+    prof_begin(kProfBackward, st);
     kern<<<(unsigned)blocks, BLOCK, smem, st>>>((const T*)points, (const T*)As, (const T*)gout, (T*)G,
                                                 (T*)dpoints, nP, broadcast, nsteps, g, chunks, chunk_pts);
+    prof_end(kProfBackward, st);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -590,7 +611,7 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
 {
     const int D = g.n_cells * Dim<NDIM>::kPpc;
     CPAB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)n_theta * D * sizeof(T), st));
-    bool fits = false;
+    bool fits = nP == 0;      // nothing to integrate: G stays zero, the epilogue writes dtheta = 0
     int rc = kOk;
 #define TRY(SEG, SMEM, BLOCK)                                                                      \
     if (!fits && rc == kOk)                                                                        \
@@ -617,7 +638,10 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
     }
     constexpr int TT = 8;
     dim3 grid((unsigned)((n_theta + TT - 1) / TT), (unsigned)((d + 127) / 128));
+    prof_begin(kProfEpilogue, st);
     k_grad_epilogue<T, TT><<<grid, 128, 0, st>>>((const T*)ws, (const T*)basis, (T*)dtheta, n_theta, D, d);
+    prof_end(kProfEpilogue, st);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }

@@ -344,8 +344,11 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
             }
             return kOk;
         }
+        prof_begin(backward ? kProfInterpBwd : kProfInterpFwd, st);
         if (!backward) k_interp_fwd_1d<T><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
         else k_interp_bwd_1d<T><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
+        prof_end(backward ? kProfInterpBwd : kProfInterpFwd, st);
+        count_launch();
         CPAB_CUDA_OK(cudaGetLastError());
         return kOk;
     }
@@ -353,6 +356,7 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
     const unsigned gy = (unsigned)((s.O[ndim - 1] + TILE - 1) / TILE);
     if (z > 65535 || gy > 65535) { set_error("interpolate: batch x middle extent %ld exceeds 65535", z); return kErrUnsupported; }
     dim3 g((unsigned)((s.O[0] + TILE - 1) / TILE), gy, (unsigned)z);
+    prof_begin(backward ? kProfInterpBwd : kProfInterpFwd, st);
     if (ndim == 2) {
         if (!backward) k_interp_fwd<T, 2><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
         else k_interp_bwd<T, 2><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
@@ -360,6 +364,8 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
         if (!backward) k_interp_fwd<T, 3><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
         else k_interp_bwd<T, 3><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
     }
+    prof_end(backward ? kProfInterpBwd : kProfInterpFwd, st);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }

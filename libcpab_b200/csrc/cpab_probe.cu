@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) k_fma_probe(float* out, int iters, float 
 int launch_fma_probe(int blocks, int iters, float* out, cudaStream_t st)
 {
     k_fma_probe<<<blocks, 256, 0, st>>>(out, iters, 0.999f, 0.001f);
+    count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }

@@ -321,7 +321,9 @@ def expm_pade13(A: np.ndarray) -> np.ndarray:
     nsq = np.maximum(dt.type(0.0), np.ceil(lg)).astype(dt)
     As = (A / (dt.type(2.0) ** nsq)).astype(dt)
     nsq = nsq.reshape(-1).astype(np.int64)
-    b = np.asarray(_PADE13, dtype=dt)
+    # the reference builds the coefficients as a float32 tensor and then casts (expm.py:44-48:
+    # `torch.Tensor([...]).type(A.dtype)`), so even its float64 expm sees float32-rounded b_k
+    b = np.asarray(_PADE13, dtype=np.float32).astype(dt)
     I = np.eye(m, dtype=dt)
     A2 = As @ As
     A4 = A2 @ A2

@@ -52,3 +52,15 @@ def bs_of(B, nc, dtype=np.float32):
     ndim = len(nc)
     nC = int({1: 1, 2: 4, 3: 5}[ndim] * np.prod(nc))
     return np.ascontiguousarray(np.asarray(B).astype(dtype).T.reshape(B.shape[1], nC, ndim, ndim + 1))
+
+
+def flow_gain(As):
+    """exp(max_c ||A_c,lin||_inf): how much the unit-time flow can amplify a perturbation of a
+    point (Gronwall).  A rounding difference of 1 ulp per step (FMA contraction, or Trels rounded
+    differently in the last bit) is amplified by up to this factor over the 50 steps, so any
+    comparison that is not bit-exact by construction is held to 1e-5 * flow_gain, not 1e-5:
+    the reference's own float32 extension and float64 numpy backend differ by 4.4e-5 on BASELINE
+    configs[0] for the same reason."""
+    A = np.asarray(As, dtype=np.float64)
+    n = A.shape[-2]
+    return float(np.exp(np.abs(A[..., :n]).sum(-1).max()))

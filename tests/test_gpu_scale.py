@@ -76,11 +76,11 @@ def test_full_size_gradient_properties(tess, n_theta, size, kw):
     assert rel_err((da + db).cpu().numpy(), d1.cpu().numpy()) < 2e-5
     # tiling variants agree
     try:
-        _lib.set_tuning("bwd_seg", 5)
+        _lib.set_tuning("bwd_seg", 10)
         _lib.set_tuning("chunk_pts", 512)
         dv, _ = ops.backward_theta(grid, As, B, g1, tess, 50)
     finally:
-        _lib.set_tuning("bwd_seg", 10)
+        _lib.set_tuning("bwd_seg", 5)
         _lib.set_tuning("chunk_pts", 2048)
     assert rel_err(dv.cpu().numpy(), d1.cpu().numpy()) < 2e-5
     # oracle on a sub-sample of points, first theta

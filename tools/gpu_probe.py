@@ -97,7 +97,7 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
                     _lib.set_tuning("bwd_block", block)
                     _lib.set_tuning("chunk_pts", chunk)
                     bwd_line(f"seg{seg}_block{block}_chunk{chunk}")
-        _lib.set_tuning("bwd_seg", 10)
+        _lib.set_tuning("bwd_seg", 5)
         _lib.set_tuning("bwd_block", 128)
         _lib.set_tuning("chunk_pts", 2048)
 
