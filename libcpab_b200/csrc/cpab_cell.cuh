@@ -103,7 +103,10 @@ inline Geom make_geom(int ndim, const int* nc)
 // kf is returned as a float holding the integer.
 CPAB_HD void divmod_exact(float p, float nf, float w, float& kf, float& r)
 {
-    const float kMagic = 12582912.0f;                       // 1.5 * 2^23
+    float kMagic = 12582912.0f;                             // 1.5 * 2^23
+#if defined(__CUDA_ARCH__)
+    asm("" : "+f"(kMagic));   // keep it in a register: FFMA takes one non-register operand, let that be n
+#endif
     const float t = fmaf(p, nf, kMagic);
     kf = t - kMagic;
     r = fmaf(-kf, w, p);

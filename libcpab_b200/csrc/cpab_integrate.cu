@@ -25,6 +25,16 @@
 
 #include "cpab_common.cuh"
 
+// -DCPAB_FAST_BUILD instantiates only the float32 2-D kernels (SASS experiments; never shipped).
+#ifdef CPAB_FAST_BUILD
+#define CPAB_DISPATCH(T1D, T2D, T3D) (T2D)
+#define CPAB_DTYPE(F, D) (F)
+#else
+#define CPAB_DISPATCH(T1D, T2D, T3D) (g.ndim == 1 ? (T1D) : g.ndim == 2 ? (T2D) : (T3D))
+#define CPAB_DTYPE(F, D) (dtype == kF32 ? (F) : (D))
+#endif
+
+
 namespace cpab {
 
 // ---- rounding-controlled scalar ops ---------------------------------------------------------------
@@ -61,6 +71,44 @@ template <int NDIM> __device__ __forceinline__ void load_affine(const double* M,
 #pragma unroll
     for (int i = 0; i < Dim<NDIM>::kPpc / 2; ++i) { const double2 t = v[i]; a[2*i] = t.x; a[2*i+1] = t.y; }
 }
+
+// Per-theta table of per-cell matrices: shared memory (32-bit shared-window address, explicit
+// ld.shared so that the address arithmetic is one IMAD per step) or, for tessellations too large
+// to stage, global memory through the read-only path.
+__device__ __forceinline__ void lds_vec(uint32_t addr, float* a, int n4, int n2)
+{
+    for (int i = 0; i < n4; ++i)
+        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+            : "=f"(a[4 * i]), "=f"(a[4 * i + 1]), "=f"(a[4 * i + 2]), "=f"(a[4 * i + 3]) : "r"(addr + 16 * i));
+    for (int i = 0; i < n2; ++i)
+        asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a[2 * i]), "=f"(a[2 * i + 1]) : "r"(addr + 8 * i));
+}
+__device__ __forceinline__ void lds_vec(uint32_t addr, double* a, int n4, int n2)
+{
+    (void)n4;
+    for (int i = 0; i < n2; ++i)
+        asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a[2 * i]), "=d"(a[2 * i + 1]) : "r"(addr + 16 * i));
+}
+
+template <typename T, int NDIM, bool SMEM> struct CellTable {
+    static constexpr int PPC = Dim<NDIM>::kPpc;
+    const T* gptr;
+    uint32_t saddr;
+    __device__ __forceinline__ void load(int c, T* a) const
+    {
+        if (SMEM) {
+            const uint32_t addr = saddr + (uint32_t)c * (uint32_t)(PPC * sizeof(T));
+            if (sizeof(T) == 4 && NDIM == 3) {
+#pragma unroll
+                for (int i = 0; i < 1; ++i) lds_vec(addr, a, 3, 0);
+            } else {
+                lds_vec(addr, a, 0, PPC / 2);
+            }
+        } else {
+            load_affine<NDIM>(gptr + (size_t)c * PPC, a);
+        }
+    }
+};
 
 // out = A [v;1] in the reference's left-to-right order with every product and sum rounded
 // (cpab_ops.cpp:192-206) -- bit-identical to the CPU reference.
@@ -133,7 +181,7 @@ __global__ void __launch_bounds__(256) k_findcellidx(const T* __restrict__ pts, 
 // forward: nsteps x { c = cell(p) ; p = Trels[theta][c] [p;1] }
 // =====================================================================================================
 template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 4 : 1))
 k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restrict__ out, long nP,
           int broadcast, int nsteps, const __grid_constant__ Geom g, int chunks, int chunk_pts)
 {
@@ -142,12 +190,14 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
     const int theta = blockIdx.x / chunks;
     const int chunk = blockIdx.x - theta * chunks;
     const int tsize = g.n_cells * PPC;
-    const T* Tm = trels + (size_t)theta * tsize;
+    CellTable<T, NDIM, SMEM> tab;
+    tab.gptr = trels + (size_t)theta * tsize;
+    tab.saddr = 0;
     if (SMEM) {
         T* sT = reinterpret_cast<T*>(smem_raw);
-        stage_block(sT, Tm, tsize);
+        stage_block(sT, tab.gptr, tsize);
         __syncthreads();
-        Tm = sT;
+        tab.saddr = (uint32_t)__cvta_generic_to_shared(sT);
     }
     const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
     T* dst = out + (size_t)theta * NDIM * nP;
@@ -167,7 +217,7 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
             for (int u = 0; u < PPT; ++u) {
                 const int c = find_cell<NDIM>(p[u], g);
                 T a[PPC], q[NDIM];
-                load_affine<NDIM>(Tm + c * PPC, a);
+                tab.load(c, a);
                 if (STRICT) affine_strict<NDIM>(a, p[u], q); else affine_fma<NDIM>(a, p[u], q);
 #pragma unroll
                 for (int j = 0; j < NDIM; ++j) p[u][j] = q[j];
@@ -265,8 +315,42 @@ __device__ __forceinline__ void rk2_step(const T* A, T* p, T h, T hh)
     for (int j = 0; j < NDIM; ++j) p[j] = Num<T>::fma(h, vm[j], p[j]);
 }
 
+// Final flush of the per-thread accumulators: the lanes of a warp are neighbouring points, so they
+// mostly end in the same one to three cells.  Runs of equal cell index are summed with a segmented
+// shuffle scan and only the last lane of each run issues the (native, fire-and-forget) global
+// reductions.  Must be called by all 32 lanes; lanes without a trajectory pass key = -1.
+template <typename T, int PPC>
+__device__ __forceinline__ void flush_runs(T* __restrict__ Gg, int key, T* acc)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int prev = __shfl_up_sync(full, key, 1);
+    const unsigned heads = __ballot_sync(full, lane == 0 || prev != key);
+    const unsigned upto = heads & (full >> (31 - lane));           // heads at or below this lane
+    const int start = 31 - __clz(upto);
+    const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
+    const bool tail = above == 0u || (above & 1u);                 // next lane starts a new run
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+        for (int e = 0; e < PPC; ++e) {
+            const T t = __shfl_up_sync(full, acc[e], off);
+            if (lane - off >= start) acc[e] += t;
+        }
+    }
+    if (tail && key >= 0) {
+#pragma unroll
+        for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gg + (size_t)key * PPC + e, acc[e]);
+    }
+}
+
+// resident CTAs per SM the register allocation is tuned for (float: ~80 regs in 1-D/2-D, ~100 in 3-D)
+template <typename T, int NDIM, int BLOCK> struct BwdOcc {
+    static constexpr int kMinBlocks = sizeof(T) == 8 ? 1 : 65536 / (BLOCK * (NDIM == 3 ? 102 : 80));
+};
+
 template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, (BwdOcc<T, NDIM, BLOCK>::kMinBlocks))
 k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __restrict__ gout,
            T* __restrict__ G, T* __restrict__ dpoints, long nP, int broadcast, int nsteps,
            const __grid_constant__ Geom g, int chunks, int chunk_pts)
@@ -278,142 +362,136 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     const int tsize = g.n_cells * PPC;
     const int nseg = (nsteps + SEG - 1) / SEG;
 
-    // shared layout: [A block][G block] (if SMEM), checkpoints [nseg][NDIM][BLOCK],
-    // cell trace [nsteps][BLOCK] (16-bit when the tessellation has < 65536 simplices)
+    // shared layout: [A block] (if SMEM), checkpoints [nseg][NDIM][BLOCK], cell trace
+    // [nsteps][BLOCK] (16-bit; 32-bit only for tessellations of >= 65536 simplices, which never
+    // fit the staged path)
     T* sA = reinterpret_cast<T*>(smem_raw);
-    T* sG = sA + (SMEM ? tsize : 0);
-    T* ck = sG + (SMEM ? tsize : 0);
+    T* ck = sA + (SMEM ? tsize : 0);
     unsigned short* ct16 = reinterpret_cast<unsigned short*>(ck + (size_t)nseg * NDIM * BLOCK);
     int* ct32 = reinterpret_cast<int*>(ct16);
-    const bool wide = g.n_cells > 65535;
-    const T* Am = As + (size_t)theta * tsize;
-    T* Gm = G + (size_t)theta * tsize;
+    const bool wide = !SMEM && g.n_cells > 65535;
+    CellTable<T, NDIM, SMEM> tab;
+    tab.gptr = As + (size_t)theta * tsize;
+    tab.saddr = 0;
     if (SMEM) {
-        stage_block(sA, Am, tsize);
-        for (int i = threadIdx.x; i < tsize; i += BLOCK) sG[i] = 0;
+        stage_block(sA, tab.gptr, tsize);
         __syncthreads();
-        Am = sA;
-        Gm = sG;
+        tab.saddr = (uint32_t)__cvta_generic_to_shared(sA);
     }
+    T* Gg = G + (size_t)theta * tsize;
     const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
     const T* gsrc = gout + (size_t)theta * NDIM * nP;
     const long begin = (long)chunk * chunk_pts;
     const long end = begin + chunk_pts < nP ? begin + chunk_pts : nP;
     const T h = (T)(1.0 / nsteps), hh = (T)(0.5 / nsteps), h2 = (T)(0.5 / nsteps / nsteps);
 
-    for (long i = begin + threadIdx.x; i < end; i += BLOCK) {
-        T p[NDIM], lam[NDIM];
-#pragma unroll
-        for (int j = 0; j < NDIM; ++j) { p[j] = src[i + (long)j * nP]; lam[j] = gsrc[i + (long)j * nP]; }
-
-        // ---- pass 1: the RK2 trajectory.  Records the cell of every step and a checkpoint of p
-        //      at the start of every segment; this is the only pass that searches cells.
-        for (int sg = 0; sg < nseg; ++sg) {
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j) ck[(sg * NDIM + j) * BLOCK + threadIdx.x] = p[j];
-#pragma unroll
-            for (int s = 0; s < SEG; ++s) {
-                const int n = sg * SEG + s;
-                if (n < nsteps) {
-                    const int c = find_cell<NDIM>(p, g);
-                    if (wide) ct32[n * BLOCK + threadIdx.x] = c;
-                    else ct16[n * BLOCK + threadIdx.x] = (unsigned short)c;
-                    if (n + 1 < nsteps) {
-                        T a[PPC];
-                        load_affine<NDIM>(Am + c * PPC, a);
-                        rk2_step<NDIM>(a, p, h, hh);
-                    }
-                }
-            }
-        }
-
-        // ---- pass 2: segments in reverse; replay p into registers (no search), sweep lambda back
+    for (long base = begin; base < end; base += BLOCK) {      // warp-uniform trip count
+        const long i = base + threadIdx.x;
+        const bool valid = i < end;
         T acc[PPC];
         int cur = -1;
 #pragma unroll
         for (int e = 0; e < PPC; ++e) acc[e] = 0;
-        for (int sg = nseg - 1; sg >= 0; --sg) {
-            const int len = (nsteps - sg * SEG) < SEG ? (nsteps - sg * SEG) : SEG;
-            T ps[SEG][NDIM];
-            int cs[SEG];
+        if (valid) {
+            T p[NDIM], lam[NDIM];
 #pragma unroll
-            for (int j = 0; j < NDIM; ++j) p[j] = ck[(sg * NDIM + j) * BLOCK + threadIdx.x];
+            for (int j = 0; j < NDIM; ++j) { p[j] = src[i + (long)j * nP]; lam[j] = gsrc[i + (long)j * nP]; }
+
+            // ---- pass 1: the RK2 trajectory.  Records the cell of every step and a checkpoint
+            //      of p at the start of every segment; the only pass that searches cells.
+            for (int sg = 0; sg < nseg; ++sg) {
 #pragma unroll
-            for (int s = 0; s < SEG; ++s) {
-                if (s < len) {
+                for (int j = 0; j < NDIM; ++j) ck[(sg * NDIM + j) * BLOCK + threadIdx.x] = p[j];
+#pragma unroll
+                for (int s = 0; s < SEG; ++s) {
                     const int n = sg * SEG + s;
-                    cs[s] = wide ? ct32[n * BLOCK + threadIdx.x] : (int)ct16[n * BLOCK + threadIdx.x];
-#pragma unroll
-                    for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
-                    if (s + 1 < len) {
-                        T a[PPC];
-                        load_affine<NDIM>(Am + cs[s] * PPC, a);
-                        rk2_step<NDIM>(a, p, h, hh);
+                    if (n < nsteps) {
+                        const int c = find_cell<NDIM>(p, g);
+                        if (wide) ct32[n * BLOCK + threadIdx.x] = c;
+                        else ct16[n * BLOCK + threadIdx.x] = (unsigned short)c;
+                        if (n + 1 < nsteps) {
+                            T a[PPC];
+                            tab.load(c, a);
+                            rk2_step<NDIM>(a, p, h, hh);
+                        }
                     }
                 }
             }
+
+            // ---- pass 2: segments in reverse; replay p into registers (no search), sweep back
+            for (int sg = nseg - 1; sg >= 0; --sg) {
+                const int len = (nsteps - sg * SEG) < SEG ? (nsteps - sg * SEG) : SEG;
+                T ps[SEG][NDIM];
+                int cs[SEG];
 #pragma unroll
-            for (int s = SEG - 1; s >= 0; --s) {
-                if (s < len) {
-                    const int c = cs[s];
-                    T a[PPC], v[NDIM], pm[NDIM], w[NDIM];
-                    load_affine<NDIM>(Am + c * PPC, a);
-                    affine_fma<NDIM>(a, ps[s], v);
+                for (int j = 0; j < NDIM; ++j) p[j] = ck[(sg * NDIM + j) * BLOCK + threadIdx.x];
 #pragma unroll
-                    for (int j = 0; j < NDIM; ++j) pm[j] = Num<T>::fma(hh, v[j], ps[s][j]);
-                    // w = A_lin^T lambda
+                for (int s = 0; s < SEG; ++s) {
+                    if (s < len) {
+                        const int n = sg * SEG + s;
+                        cs[s] = wide ? ct32[n * BLOCK + threadIdx.x] : (int)ct16[n * BLOCK + threadIdx.x];
 #pragma unroll
-                    for (int r = 0; r < NDIM; ++r) {
-                        T t = 0;
-#pragma unroll
-                        for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], lam[j], t);
-                        w[r] = t;
+                        for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
+                        if (s + 1 < len) {
+                            T a[PPC];
+                            tab.load(cs[s], a);
+                            rk2_step<NDIM>(a, p, h, hh);
+                        }
                     }
-                    if (c != cur) {
-                        if (cur >= 0) {
+                }
 #pragma unroll
-                            for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gm + cur * PPC + e, acc[e]);
+                for (int s = SEG - 1; s >= 0; --s) {
+                    if (s < len) {
+                        const int c = cs[s];
+                        T a[PPC], v[NDIM], pm[NDIM], w[NDIM];
+                        tab.load(c, a);
+                        affine_fma<NDIM>(a, ps[s], v);
+#pragma unroll
+                        for (int j = 0; j < NDIM; ++j) pm[j] = Num<T>::fma(hh, v[j], ps[s][j]);
+                        // w = A_lin^T lambda
+#pragma unroll
+                        for (int r = 0; r < NDIM; ++r) {
+                            T t = a[r] * lam[0];
+#pragma unroll
+                            for (int j = 1; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], lam[j], t);
+                            w[r] = t;
+                        }
+                        if (c != cur) {                 // left a cell: hand its sum to G[theta]
+                            if (cur >= 0) {
+#pragma unroll
+                                for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gg + (size_t)cur * PPC + e, acc[e]);
+                            }
+#pragma unroll
+                            for (int e = 0; e < PPC; ++e) acc[e] = 0;
+                            cur = c;
                         }
 #pragma unroll
-                        for (int e = 0; e < PPC; ++e) acc[e] = 0;
-                        cur = c;
-                    }
+                        for (int r = 0; r < NDIM; ++r) {
+                            const T hl = h * lam[r], hw = h2 * w[r];
 #pragma unroll
-                    for (int r = 0; r < NDIM; ++r) {
-                        const T hl = h * lam[r], hw = h2 * w[r];
+                            for (int cc = 0; cc < NDIM; ++cc)
+                                acc[r * (NDIM + 1) + cc] =
+                                    Num<T>::fma(hl, pm[cc], Num<T>::fma(hw, ps[s][cc], acc[r * (NDIM + 1) + cc]));
+                            acc[r * (NDIM + 1) + NDIM] += hl + hw;
+                        }
+                        // lambda <- lambda + h w + (h^2/2) A_lin^T w
 #pragma unroll
-                        for (int cc = 0; cc < NDIM; ++cc)
-                            acc[r * (NDIM + 1) + cc] += Num<T>::fma(hl, pm[cc], hw * ps[s][cc]);
-                        acc[r * (NDIM + 1) + NDIM] += hl + hw;
-                    }
-                    // lambda <- lambda + h w + (h^2/2) A_lin^T w
+                        for (int r = 0; r < NDIM; ++r) {
+                            T t = a[r] * w[0];
 #pragma unroll
-                    for (int r = 0; r < NDIM; ++r) {
-                        T t = 0;
-#pragma unroll
-                        for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], w[j], t);
-                        lam[r] = Num<T>::fma(h2, t, Num<T>::fma(h, w[r], lam[r]));
+                            for (int j = 1; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], w[j], t);
+                            lam[r] = Num<T>::fma(h2, t, Num<T>::fma(h, w[r], lam[r]));
+                        }
                     }
                 }
             }
-        }
-        if (cur >= 0) {
+            if (dpoints != nullptr) {
+                T* dp = dpoints + (size_t)theta * NDIM * nP;
 #pragma unroll
-            for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gm + cur * PPC + e, acc[e]);
+                for (int j = 0; j < NDIM; ++j) dp[i + (long)j * nP] = lam[j];
+            }
         }
-        if (dpoints != nullptr) {
-            T* dp = dpoints + (size_t)theta * NDIM * nP;
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j) dp[i + (long)j * nP] = lam[j];
-        }
-    }
-    if (SMEM) {
-        __syncthreads();
-        T* Gg = G + (size_t)theta * tsize;
-        for (int e = threadIdx.x; e < tsize; e += BLOCK) {
-            const T val = sG[e];
-            if (val != (T)0) Num<T>::atomic_add(Gg + e, val);
-        }
+        flush_runs<T, PPC>(Gg, cur, acc);
     }
 }
 
@@ -485,8 +563,8 @@ static int findcellidx_t(const Geom& g, const void* points, long nP, int* out, c
 
 int launch_findcellidx(int dtype, const Geom& g, const void* points, long nP, int* out, cudaStream_t st)
 {
-#define GO(T) (g.ndim == 1 ? findcellidx_t<T, 1>(g, points, nP, out, st) : g.ndim == 2 ? findcellidx_t<T, 2>(g, points, nP, out, st) : findcellidx_t<T, 3>(g, points, nP, out, st))
-    return dtype == kF32 ? GO(float) : GO(double);
+#define GO(T) CPAB_DISPATCH((findcellidx_t<T, 1>(g, points, nP, out, st)), (findcellidx_t<T, 2>(g, points, nP, out, st)), (findcellidx_t<T, 3>(g, points, nP, out, st)))
+    return CPAB_DTYPE(GO(float), GO(double));
 #undef GO
 }
 
@@ -539,10 +617,10 @@ int launch_forward(int dtype, int flags, const Geom& g, int nsteps, int n_theta,
                    int broadcast, const void* points, const void* trels, void* out, cudaStream_t st)
 {
     if (n_theta == 0 || nP == 0) return kOk;
-#define GO(T) (g.ndim == 1 ? forward_t<T, 1>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st) \
-             : g.ndim == 2 ? forward_t<T, 2>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st) \
-                           : forward_t<T, 3>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st))
-    return dtype == kF32 ? GO(float) : GO(double);
+#define GO(T) CPAB_DISPATCH((forward_t<T, 1>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st)), \
+                            (forward_t<T, 2>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st)), \
+                            (forward_t<T, 3>(flags, g, nsteps, n_theta, nP, broadcast, points, trels, out, st)))
+    return CPAB_DTYPE(GO(float), GO(double));
 #undef GO
 }
 
@@ -564,10 +642,10 @@ int launch_jacobian(int dtype, const Geom& g, int nsteps, int n_theta, int d, lo
                     const void* points, const void* As, const void* Bs, void* jac, cudaStream_t st)
 {
     if (n_theta == 0 || nP == 0 || d == 0) return kOk;
-#define GO(T) (g.ndim == 1 ? jacobian_t<T, 1>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st) \
-             : g.ndim == 2 ? jacobian_t<T, 2>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st) \
-                           : jacobian_t<T, 3>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st))
-    return dtype == kF32 ? GO(float) : GO(double);
+#define GO(T) CPAB_DISPATCH((jacobian_t<T, 1>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st)), \
+                            (jacobian_t<T, 2>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st)), \
+                            (jacobian_t<T, 3>(g, nsteps, n_theta, d, nP, broadcast, points, As, Bs, jac, st)))
+    return CPAB_DTYPE(GO(float), GO(double));
 #undef GO
 }
 
@@ -586,7 +664,7 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
     pick_chunks(nP, chunks, chunk_pts);
     const int nseg = (nsteps + SEG - 1) / SEG;
     const size_t tbytes = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
-    const size_t smem = (SMEM ? 2 * tbytes : 0) + (size_t)nseg * NDIM * BLOCK * sizeof(T) +
+    const size_t smem = (SMEM ? tbytes : 0) + (size_t)nseg * NDIM * BLOCK * sizeof(T) +
                         (size_t)nsteps * BLOCK * (g.n_cells > 65535 ? 4 : 2);
     fits = smem <= kMaxSmemBytes;
     if (!fits) return kOk;
@@ -658,10 +736,10 @@ int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta
                   backward_workspace_bytes(dtype, g, n_theta));
         return kErrWorkspace;
     }
-#define GO(T) (g.ndim == 1 ? backward_t<T, 1>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st) \
-             : g.ndim == 2 ? backward_t<T, 2>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st) \
-                           : backward_t<T, 3>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st))
-    return dtype == kF32 ? GO(float) : GO(double);
+#define GO(T) CPAB_DISPATCH((backward_t<T, 1>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)), \
+                            (backward_t<T, 2>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)), \
+                            (backward_t<T, 3>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)))
+    return CPAB_DTYPE(GO(float), GO(double));
 #undef GO
 }
 

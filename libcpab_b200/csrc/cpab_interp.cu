@@ -105,83 +105,132 @@ __device__ __forceinline__ void blend_vjp(const T* v, const T* w, T g, T* gv, T*
     for (int i = 0; i < (1 << NDIM); ++i) gv[i] = gl[i];
 }
 
-// offset of texel (t[0],t[1],t[2]) inside one [S0,S1,S2] channel plane
-template <int NDIM>
-__device__ __forceinline__ size_t texel(const int* t, const Shape& s)
+constexpr int TILE = 32;
+constexpr int REPS = TILE / 8;
+
+// Per-point sampling state shared by forward and backward: for every corner of the leading
+// NDIM-1 dimensions the 32-bit element offset of the tap pair along the LAST (memory-fastest)
+// dimension, whether that pair really is two texels (it collapses to one at a clamped border),
+// and the interpolation weights.
+template <typename T, int NDIM> struct Taps {
+    int base[1 << (NDIM - 1)];   // offset of (x?,y?,.., last = t0)
+    bool two;                    // t1 != t0 along the last dimension
+    T w[NDIM];
+};
+
+template <typename T, int NDIM>
+__device__ __forceinline__ Taps<T, NDIM> make_taps(const T* gcoord, const Shape& s)
 {
-    size_t o = t[0];
-    if (NDIM >= 2) o = o * s.S[1] + t[1];
-    if (NDIM >= 3) o = o * s.S[2] + t[2];
-    return o;
+    Taps<T, NDIM> tp;
+    int t0[NDIM], t1[NDIM];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) taps(gcoord[j], s.S[j], t0[j], t1[j], tp.w[j]);
+    tp.two = t1[NDIM - 1] != t0[NDIM - 1];
+    if (NDIM == 1) {
+        tp.base[0] = t0[0];
+    } else if (NDIM == 2) {
+        tp.base[0] = t0[0] * s.S[1] + t0[1];
+        tp.base[1] = t1[0] * s.S[1] + t0[1];
+    } else {
+        const int r00 = t0[0] * s.S[1] + t0[1], r10 = t1[0] * s.S[1] + t0[1];
+        const int dy = t1[1] - t0[1];
+        tp.base[0] = r00 * s.S[2] + t0[2];
+        tp.base[1] = r10 * s.S[2] + t0[2];
+        tp.base[2] = (r00 + dy) * s.S[2] + t0[2];
+        tp.base[3] = (r10 + dy) * s.S[2] + t0[2];
+    }
+    return tp;
 }
 
-constexpr int TILE = 32;
+// gather the 2^NDIM corner values of one channel plane (corner bit j <-> dimension j)
+template <typename T, int NDIM>
+__device__ __forceinline__ void gather(const T* __restrict__ dp, const Taps<T, NDIM>& tp, T* v)
+{
+    constexpr int H = 1 << (NDIM - 1);
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+        const T* q = dp + tp.base[u];
+        const T lo = __ldg(q);
+        v[u] = lo;
+        v[u + H] = tp.two ? __ldg(q + 1) : lo;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward.  NDIM >= 2: CTA = 256 threads, tile 32 (first index) x 32 (last index);
 // blockIdx.x -> tile along the first index, blockIdx.y -> tile along the last index,
-// blockIdx.z -> n * (middle extent) + middle index.
+// blockIdx.z -> n * (middle extent) + middle index.  All intra-sample offsets are 32-bit (the
+// host checks that one sample's grid, input and output each have < 2^31 elements); a thread owns
+// 4 points and issues all their gathers for a channel before blending.
 // ---------------------------------------------------------------------------------------------
+template <typename T, int NDIM, bool FULL>
+__device__ __forceinline__ void interp_fwd_tile(const T* __restrict__ data, const T* __restrict__ grid,
+                                                T* __restrict__ out, const Shape& s,
+                                                T (&sg)[NDIM][TILE][TILE + 1])
+{
+    constexpr int NC = 1 << NDIM;
+    const int mid = NDIM == 3 ? s.O[1] : 1;
+    const int n = blockIdx.z / mid, im = blockIdx.z - n * mid;
+    const int a0 = blockIdx.x * TILE, f0 = blockIdx.y * TILE;
+    const int O0 = s.O[0], OF = s.O[NDIM - 1];
+    const int nP = O0 * (NDIM >= 2 ? s.O[1] : 1) * (NDIM >= 3 ? s.O[2] : 1);
+    const int pstride = NDIM == 2 ? O0 : O0 * s.O[1];            // grid-point stride of the last index
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+
+    {   // phase A: unit stride along the first index
+        const T* gp = grid + (size_t)n * NDIM * nP + ((a0 + lane) + (NDIM == 3 ? O0 * im : 0) + pstride * (f0 + wrp));
+        T tmp[REPS][NDIM];
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep) {
+            const bool ok = FULL || ((a0 + lane < O0) && (f0 + wrp + 8 * rep < OF));
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) tmp[rep][j] = ok ? gp[j * nP + rep * 8 * pstride] : (T)0;
+        }
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep)
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) sg[j][wrp + 8 * rep][lane] = tmp[rep][j];
+    }
+    __syncthreads();
+
+    // phase B: a warp runs along the last index
+    const int iF = f0 + lane;
+    const int plane = s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
+    const T* dn = data + (size_t)n * s.C * plane;
+    T* on = out + (size_t)n * s.C * nP + (NDIM == 2 ? (a0 + wrp) * s.O[1] + iF
+                                                      : ((a0 + wrp) * s.O[1] + im) * s.O[2] + iF);
+    const int ostride = 8 * (NDIM == 2 ? s.O[1] : s.O[1] * s.O[2]);     // output stride of one rep
+    Taps<T, NDIM> tp[REPS];
+    bool ok[REPS];
+#pragma unroll
+    for (int rep = 0; rep < REPS; ++rep) {
+        const int a = wrp + 8 * rep;
+        ok[rep] = FULL || (a0 + a < O0 && iF < OF);
+        T gc[NDIM];
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) gc[j] = sg[j][lane][a];
+        tp[rep] = make_taps<T, NDIM>(gc, s);
+    }
+    for (int c = 0; c < s.C; ++c) {
+        const T* dp = dn + (size_t)c * plane;
+        T v[REPS][NC];
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep)
+            if (FULL || ok[rep]) gather<T, NDIM>(dp, tp[rep], v[rep]);
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep)
+            if (FULL || ok[rep]) on[(size_t)c * nP + rep * ostride] = blend<NDIM>(v[rep], tp[rep].w);
+    }
+}
+
 template <typename T, int NDIM>
 __global__ void __launch_bounds__(256)
 k_interp_fwd(const T* __restrict__ data, const T* __restrict__ grid, T* __restrict__ out, Shape s)
 {
     __shared__ T sg[NDIM][TILE][TILE + 1];
-    const int mid = NDIM == 3 ? s.O[1] : 1;
-    const int n = blockIdx.z / mid, im = blockIdx.z - n * mid;
-    const int a0 = blockIdx.x * TILE, f0 = blockIdx.y * TILE;
-    const int OF = s.O[NDIM - 1];
-    const long nP = (long)s.O[0] * (NDIM >= 2 ? s.O[1] : 1) * (NDIM >= 3 ? s.O[2] : 1);
-    const T* gn = grid + (size_t)n * NDIM * nP;
-
-    {   // phase A: unit stride along the first index
-        const int a = threadIdx.x & 31, b = threadIdx.x >> 5;
-#pragma unroll
-        for (int rep = 0; rep < TILE / 8; ++rep) {
-            const int fo = b + 8 * rep;
-            const int i0 = a0 + a, iF = f0 + fo;
-            if (i0 < s.O[0] && iF < OF) {
-                const long p = NDIM == 2 ? (long)i0 + (long)s.O[0] * iF
-                                         : (long)i0 + (long)s.O[0] * (im + (long)s.O[1] * iF);
-#pragma unroll
-                for (int j = 0; j < NDIM; ++j) sg[j][fo][a] = gn[(size_t)j * nP + p];
-            }
-        }
-    }
-    __syncthreads();
-    {   // phase B: a warp runs along the last index
-        const int fo = threadIdx.x & 31, b = threadIdx.x >> 5;
-        const int iF = f0 + fo;
-        const size_t plane = (size_t)s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
-        const size_t oplane = (size_t)nP;
-#pragma unroll
-        for (int rep = 0; rep < TILE / 8; ++rep) {
-            const int a = b + 8 * rep;
-            const int i0 = a0 + a;
-            if (i0 >= s.O[0] || iF >= OF) continue;
-            int t0[NDIM], t1[NDIM];
-            T w[NDIM];
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j) taps(sg[j][fo][a], s.S[j], t0[j], t1[j], w[j]);
-            size_t off[1 << NDIM];
-#pragma unroll
-            for (int cn = 0; cn < (1 << NDIM); ++cn) {
-                int t[3] = {0, 0, 0};
-#pragma unroll
-                for (int j = 0; j < NDIM; ++j) t[j] = ((cn >> j) & 1) ? t1[j] : t0[j];
-                off[cn] = texel<NDIM>(t, s);
-            }
-            const size_t oidx = NDIM == 2 ? (size_t)i0 * s.O[1] + iF
-                                          : ((size_t)i0 * s.O[1] + im) * s.O[2] + iF;
-            for (int c = 0; c < s.C; ++c) {
-                const T* dp = data + ((size_t)n * s.C + c) * plane;
-                T v[1 << NDIM];
-#pragma unroll
-                for (int cn = 0; cn < (1 << NDIM); ++cn) v[cn] = __ldg(dp + off[cn]);
-                out[((size_t)n * s.C + c) * oplane + oidx] = blend<NDIM>(v, w);
-            }
-        }
-    }
+    const bool full = (blockIdx.x * TILE + TILE <= s.O[0]) && (blockIdx.y * TILE + TILE <= s.O[NDIM - 1]);
+    if (full) interp_fwd_tile<T, NDIM, true>(data, grid, out, s, sg);
+    else interp_fwd_tile<T, NDIM, false>(data, grid, out, s, sg);
 }
 
 // 1-D: no transposition needed
@@ -204,94 +253,120 @@ k_interp_fwd_1d(const T* __restrict__ data, const T* __restrict__ grid, T* __res
 
 // ---------------------------------------------------------------------------------------------
 // backward: dgrid [N,NDIM,nP] (optional) and ddata [N,C,S...] (optional, accumulated atomically
-// into a zero-initialised buffer).
+// into a zero-initialised buffer).  Same tiling as the forward; the d/dgrid tile returns through
+// shared memory so that it is stored unit-stride along the first index.
 // ---------------------------------------------------------------------------------------------
+template <typename T, int NDIM, bool FULL, bool DDATA>
+__device__ __forceinline__ void interp_bwd_tile(const T* __restrict__ data, const T* __restrict__ grid,
+                                                const T* __restrict__ gout, T* __restrict__ dgrid,
+                                                T* __restrict__ ddata, const Shape& s,
+                                                T (&sg)[NDIM][TILE][TILE + 1])
+{
+    constexpr int NC = 1 << NDIM;
+    constexpr int H = 1 << (NDIM - 1);
+    const int mid = NDIM == 3 ? s.O[1] : 1;
+    const int n = blockIdx.z / mid, im = blockIdx.z - n * mid;
+    const int a0 = blockIdx.x * TILE, f0 = blockIdx.y * TILE;
+    const int O0 = s.O[0], OF = s.O[NDIM - 1];
+    const int nP = O0 * (NDIM >= 2 ? s.O[1] : 1) * (NDIM >= 3 ? s.O[2] : 1);
+    const int pstride = NDIM == 2 ? O0 : O0 * s.O[1];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const size_t goff = (size_t)n * NDIM * nP + ((a0 + lane) + (NDIM == 3 ? O0 * im : 0) + pstride * (f0 + wrp));
+
+    {
+        const T* gp = grid + goff;
+        T tmp[REPS][NDIM];
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep) {
+            const bool ok = FULL || ((a0 + lane < O0) && (f0 + wrp + 8 * rep < OF));
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) tmp[rep][j] = ok ? gp[j * nP + rep * 8 * pstride] : (T)0;
+        }
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep)
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) sg[j][wrp + 8 * rep][lane] = tmp[rep][j];
+    }
+    __syncthreads();
+
+    const int iF = f0 + lane;
+    const int plane = s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
+    const T* dn = data + (size_t)n * s.C * plane;
+    T* ddn = DDATA ? ddata + (size_t)n * s.C * plane : nullptr;
+    const T* gon = gout + (size_t)n * s.C * nP + (NDIM == 2 ? (a0 + wrp) * s.O[1] + iF
+                                                             : ((a0 + wrp) * s.O[1] + im) * s.O[2] + iF);
+    const int ostride = 8 * (NDIM == 2 ? s.O[1] : s.O[1] * s.O[2]);
+    Taps<T, NDIM> tp[REPS];
+    bool ok[REPS];
+    T dg[REPS][NDIM];
+#pragma unroll
+    for (int rep = 0; rep < REPS; ++rep) {
+        const int a = wrp + 8 * rep;
+        ok[rep] = FULL || (a0 + a < O0 && iF < OF);
+        T gc[NDIM];
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) { gc[j] = sg[j][lane][a]; dg[rep][j] = 0; }
+        tp[rep] = make_taps<T, NDIM>(gc, s);
+    }
+    for (int c = 0; c < s.C; ++c) {
+        const T* dp = dn + (size_t)c * plane;
+        T v[REPS][NC], g[REPS];
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep) {
+            if (FULL || ok[rep]) {
+                gather<T, NDIM>(dp, tp[rep], v[rep]);
+                g[rep] = gon[(size_t)c * nP + rep * ostride];
+            }
+        }
+#pragma unroll
+        for (int rep = 0; rep < REPS; ++rep) {
+            if (FULL || ok[rep]) {
+                T gv[NC], dw[NDIM];
+                blend_vjp<NDIM>(v[rep], tp[rep].w, g[rep], gv, dw);
+#pragma unroll
+                for (int j = 0; j < NDIM; ++j) dg[rep][j] += dw[j];
+                if (DDATA) {
+                    T* q = ddn + (size_t)c * plane;
+#pragma unroll
+                    for (int u = 0; u < H; ++u) {
+                        atomicAdd(q + tp[rep].base[u], gv[u]);
+                        atomicAdd(q + tp[rep].base[u] + (tp[rep].two ? 1 : 0), gv[u + H]);
+                    }
+                }
+            }
+        }
+    }
+    if (dgrid == nullptr) return;
+    // xd = x - x0 with x = g*(size-1): d/dg = size-1
+#pragma unroll
+    for (int rep = 0; rep < REPS; ++rep)
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) sg[j][lane][wrp + 8 * rep] = dg[rep][j] * (T)(s.S[j] - 1);
+    __syncthreads();
+    T* dp_out = dgrid + goff;
+#pragma unroll
+    for (int rep = 0; rep < REPS; ++rep) {
+        const bool okA = FULL || ((a0 + lane < O0) && (f0 + wrp + 8 * rep < OF));
+        if (okA) {
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) dp_out[j * nP + rep * 8 * pstride] = sg[j][wrp + 8 * rep][lane];
+        }
+    }
+}
+
 template <typename T, int NDIM>
 __global__ void __launch_bounds__(256)
 k_interp_bwd(const T* __restrict__ data, const T* __restrict__ grid, const T* __restrict__ gout,
              T* __restrict__ dgrid, T* __restrict__ ddata, Shape s)
 {
     __shared__ T sg[NDIM][TILE][TILE + 1];
-    const int mid = NDIM == 3 ? s.O[1] : 1;
-    const int n = blockIdx.z / mid, im = blockIdx.z - n * mid;
-    const int a0 = blockIdx.x * TILE, f0 = blockIdx.y * TILE;
-    const int OF = s.O[NDIM - 1];
-    const long nP = (long)s.O[0] * (NDIM >= 2 ? s.O[1] : 1) * (NDIM >= 3 ? s.O[2] : 1);
-    const T* gn = grid + (size_t)n * NDIM * nP;
-    const int a_ld = threadIdx.x & 31, b_ld = threadIdx.x >> 5;
-
-#pragma unroll
-    for (int rep = 0; rep < TILE / 8; ++rep) {
-        const int fo = b_ld + 8 * rep;
-        const int i0 = a0 + a_ld, iF = f0 + fo;
-        if (i0 < s.O[0] && iF < OF) {
-            const long p = NDIM == 2 ? (long)i0 + (long)s.O[0] * iF
-                                     : (long)i0 + (long)s.O[0] * (im + (long)s.O[1] * iF);
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j) sg[j][fo][a_ld] = gn[(size_t)j * nP + p];
-        }
-    }
-    __syncthreads();
-    {
-        const int fo = threadIdx.x & 31, b = threadIdx.x >> 5;
-        const int iF = f0 + fo;
-        const size_t plane = (size_t)s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
-        const size_t oplane = (size_t)nP;
-#pragma unroll
-        for (int rep = 0; rep < TILE / 8; ++rep) {
-            const int a = b + 8 * rep;
-            const int i0 = a0 + a;
-            if (i0 >= s.O[0] || iF >= OF) continue;
-            int t0[NDIM], t1[NDIM];
-            T w[NDIM];
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j) taps(sg[j][fo][a], s.S[j], t0[j], t1[j], w[j]);
-            size_t off[1 << NDIM];
-#pragma unroll
-            for (int cn = 0; cn < (1 << NDIM); ++cn) {
-                int t[3] = {0, 0, 0};
-#pragma unroll
-                for (int j = 0; j < NDIM; ++j) t[j] = ((cn >> j) & 1) ? t1[j] : t0[j];
-                off[cn] = texel<NDIM>(t, s);
-            }
-            const size_t oidx = NDIM == 2 ? (size_t)i0 * s.O[1] + iF
-                                          : ((size_t)i0 * s.O[1] + im) * s.O[2] + iF;
-            T dg[NDIM];
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j) dg[j] = 0;
-            for (int c = 0; c < s.C; ++c) {
-                const size_t ch = (size_t)n * s.C + c;
-                const T* dp = data + ch * plane;
-                const T g = gout[ch * oplane + oidx];
-                T v[1 << NDIM], gv[1 << NDIM], dw[NDIM];
-#pragma unroll
-                for (int cn = 0; cn < (1 << NDIM); ++cn) v[cn] = __ldg(dp + off[cn]);
-                blend_vjp<NDIM>(v, w, g, gv, dw);
-#pragma unroll
-                for (int j = 0; j < NDIM; ++j) dg[j] += dw[j];
-                if (ddata != nullptr) {
-#pragma unroll
-                    for (int cn = 0; cn < (1 << NDIM); ++cn) atomicAdd(ddata + ch * plane + off[cn], gv[cn]);
-                }
-            }
-            // xd = x - x0 with x = g*(size-1): d/dg = size-1
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j) sg[j][fo][a] = dg[j] * (T)(s.S[j] - 1);
-        }
-    }
-    if (dgrid == nullptr) return;
-    __syncthreads();
-    T* dn = dgrid + (size_t)n * NDIM * nP;
-#pragma unroll
-    for (int rep = 0; rep < TILE / 8; ++rep) {
-        const int fo = b_ld + 8 * rep;
-        const int i0 = a0 + a_ld, iF = f0 + fo;
-        if (i0 < s.O[0] && iF < OF) {
-            const long p = NDIM == 2 ? (long)i0 + (long)s.O[0] * iF
-                                     : (long)i0 + (long)s.O[0] * (im + (long)s.O[1] * iF);
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j) dn[(size_t)j * nP + p] = sg[j][fo][a_ld];
-        }
+    const bool full = (blockIdx.x * TILE + TILE <= s.O[0]) && (blockIdx.y * TILE + TILE <= s.O[NDIM - 1]);
+    if (ddata != nullptr) {
+        if (full) interp_bwd_tile<T, NDIM, true, true>(data, grid, gout, dgrid, ddata, s, sg);
+        else interp_bwd_tile<T, NDIM, false, true>(data, grid, gout, dgrid, ddata, s, sg);
+    } else {
+        if (full) interp_bwd_tile<T, NDIM, true, false>(data, grid, gout, dgrid, ddata, s, sg);
+        else interp_bwd_tile<T, NDIM, false, false>(data, grid, gout, dgrid, ddata, s, sg);
     }
 }
 
@@ -351,6 +426,14 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
         count_launch();
         CPAB_CUDA_OK(cudaGetLastError());
         return kOk;
+    }
+    {   // the kernels index one sample with 32-bit offsets
+        long long gridpts = 1, inpts = s.C;
+        for (int j = 0; j < ndim; ++j) { gridpts *= s.O[j]; inpts *= s.S[j]; }
+        if (gridpts * ndim >= (1LL << 31) || inpts >= (1LL << 31) || gridpts * s.C >= (1LL << 31)) {
+            set_error("interpolate: one sample exceeds 2^31 elements");
+            return kErrUnsupported;
+        }
     }
     const long z = (long)s.N * (ndim == 3 ? s.O[1] : 1);
     const unsigned gy = (unsigned)((s.O[ndim - 1] + TILE - 1) / TILE);
