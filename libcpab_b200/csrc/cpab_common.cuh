@@ -40,6 +40,7 @@ bool prof_begin(int slot, cudaStream_t st);   // true if an event was recorded
 void prof_end(int slot, cudaStream_t st);
 
 int set_tuning(const char* key, int value);
+void set_interp_variant(int v);   // cpab_interp.cu
 const char* get_error();
 
 #define CPAB_CUDA_OK(expr)                                                                   \

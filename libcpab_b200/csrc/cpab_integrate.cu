@@ -328,8 +328,7 @@ __device__ __forceinline__ void flush_runs(T* __restrict__ Gg, int key, T* acc)
     const unsigned heads = __ballot_sync(full, lane == 0 || prev != key);
     const unsigned upto = heads & (full >> (31 - lane));           // heads at or below this lane
     const int start = 31 - __clz(upto);
-    const unsigned above = lane == 31 ? 0u : (heads >> (lane + 1));
-    const bool tail = above == 0u || (above & 1u);                 // next lane starts a new run
+    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);  // next lane starts a new run
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
 #pragma unroll
@@ -546,6 +545,7 @@ int set_tuning(const char* key, int value)
     if (k == "chunk_pts" && value >= 256 && value % 256 == 0) { g_tune_chunk_pts = value; return kOk; }
     if (k == "bwd_seg" && (value == 5 || value == 10)) { g_tune_bwd_seg = value; return kOk; }
     if (k == "bwd_block" && (value == 64 || value == 128 || value == 256)) { g_tune_bwd_block = value; return kOk; }
+    if (k == "interp_variant" && value >= 0 && value <= 2) { set_interp_variant(value); return kOk; }
     set_error("unknown tuning key/value %s=%d", key, value);
     return kErrArgument;
 }

@@ -37,6 +37,8 @@ template <> struct R<double> {
     static __device__ __forceinline__ double flo(double a) { return floor(a); }
 };
 
+int g_interp_variant = 0;   // experiment knob (cpab_b200_set_tuning "interp_variant")
+
 struct Shape {
     int N, C;
     int S[3];   // input spatial sizes  (W, H, D)
@@ -163,7 +165,7 @@ __device__ __forceinline__ void gather(const T* __restrict__ dp, const Taps<T, N
 // host checks that one sample's grid, input and output each have < 2^31 elements); a thread owns
 // 4 points and issues all their gathers for a channel before blending.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NDIM, bool FULL>
+template <typename T, int NDIM, bool FULL, int BATCH>
 __device__ __forceinline__ void interp_fwd_tile(const T* __restrict__ data, const T* __restrict__ grid,
                                                 T* __restrict__ out, const Shape& s,
                                                 T (&sg)[NDIM][TILE][TILE + 1])
@@ -193,44 +195,49 @@ __device__ __forceinline__ void interp_fwd_tile(const T* __restrict__ data, cons
     }
     __syncthreads();
 
-    // phase B: a warp runs along the last index
+    // phase B: a warp runs along the last index; BATCH points per thread are in flight at a time
     const int iF = f0 + lane;
     const int plane = s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
     const T* dn = data + (size_t)n * s.C * plane;
     T* on = out + (size_t)n * s.C * nP + (NDIM == 2 ? (a0 + wrp) * s.O[1] + iF
                                                       : ((a0 + wrp) * s.O[1] + im) * s.O[2] + iF);
     const int ostride = 8 * (NDIM == 2 ? s.O[1] : s.O[1] * s.O[2]);     // output stride of one rep
-    Taps<T, NDIM> tp[REPS];
-    bool ok[REPS];
 #pragma unroll
-    for (int rep = 0; rep < REPS; ++rep) {
-        const int a = wrp + 8 * rep;
-        ok[rep] = FULL || (a0 + a < O0 && iF < OF);
-        T gc[NDIM];
+    for (int r0 = 0; r0 < REPS; r0 += BATCH) {
+        Taps<T, NDIM> tp[BATCH];
+        bool ok[BATCH];
 #pragma unroll
-        for (int j = 0; j < NDIM; ++j) gc[j] = sg[j][lane][a];
-        tp[rep] = make_taps<T, NDIM>(gc, s);
-    }
-    for (int c = 0; c < s.C; ++c) {
-        const T* dp = dn + (size_t)c * plane;
-        T v[REPS][NC];
+        for (int b = 0; b < BATCH; ++b) {
+            const int a = wrp + 8 * (r0 + b);
+            ok[b] = FULL || (a0 + a < O0 && iF < OF);
+            T gc[NDIM];
 #pragma unroll
-        for (int rep = 0; rep < REPS; ++rep)
-            if (FULL || ok[rep]) gather<T, NDIM>(dp, tp[rep], v[rep]);
+            for (int j = 0; j < NDIM; ++j) gc[j] = sg[j][lane][a];
+            tp[b] = make_taps<T, NDIM>(gc, s);
+        }
+        for (int c = 0; c < s.C; ++c) {
+            const T* dp = dn + (size_t)c * plane;
+            T v[BATCH][NC];
 #pragma unroll
-        for (int rep = 0; rep < REPS; ++rep)
-            if (FULL || ok[rep]) on[(size_t)c * nP + rep * ostride] = blend<NDIM>(v[rep], tp[rep].w);
+            for (int b = 0; b < BATCH; ++b)
+                if (FULL || ok[b]) gather<T, NDIM>(dp, tp[b], v[b]);
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b)
+                if (FULL || ok[b]) on[(size_t)c * nP + (r0 + b) * ostride] = blend<NDIM>(v[b], tp[b].w);
+        }
     }
 }
 
-template <typename T, int NDIM>
-__global__ void __launch_bounds__(256)
+// BATCH = points per thread whose gathers are in flight together; MINB = resident CTAs per SM
+// the register allocation targets (more CTAs hide the two dependent memory round trips per tile)
+template <typename T, int NDIM, int BATCH, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_interp_fwd(const T* __restrict__ data, const T* __restrict__ grid, T* __restrict__ out, Shape s)
 {
     __shared__ T sg[NDIM][TILE][TILE + 1];
     const bool full = (blockIdx.x * TILE + TILE <= s.O[0]) && (blockIdx.y * TILE + TILE <= s.O[NDIM - 1]);
-    if (full) interp_fwd_tile<T, NDIM, true>(data, grid, out, s, sg);
-    else interp_fwd_tile<T, NDIM, false>(data, grid, out, s, sg);
+    if (full) interp_fwd_tile<T, NDIM, true, BATCH>(data, grid, out, s, sg);
+    else interp_fwd_tile<T, NDIM, false, BATCH>(data, grid, out, s, sg);
 }
 
 // 1-D: no transposition needed
@@ -441,10 +448,17 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
     dim3 g((unsigned)((s.O[0] + TILE - 1) / TILE), gy, (unsigned)z);
     prof_begin(backward ? kProfInterpBwd : kProfInterpFwd, st);
     if (ndim == 2) {
-        if (!backward) k_interp_fwd<T, 2><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+        if (!backward) {
+            if (sizeof(T) == 4 && g_interp_variant == 1) k_interp_fwd<T, 2, 2, 6><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+            else if (sizeof(T) == 4 && g_interp_variant == 2) k_interp_fwd<T, 2, 1, 8><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+            else k_interp_fwd<T, 2, 4, 1><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+        }
         else k_interp_bwd<T, 2><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
     } else {
-        if (!backward) k_interp_fwd<T, 3><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+        if (!backward) {
+            if (sizeof(T) == 4 && g_interp_variant >= 1) k_interp_fwd<T, 3, 1, 4><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+            else k_interp_fwd<T, 3, 2, 1><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+        }
         else k_interp_bwd<T, 3><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
     }
     prof_end(backward ? kProfInterpBwd : kProfInterpFwd, st);
@@ -462,6 +476,8 @@ Shape make_shape(int ndim, int N, int C, const int* in_size, const int* out_size
 }
 
 }  // namespace
+
+void set_interp_variant(int v) { g_interp_variant = v; }
 
 int launch_interp_forward(int dtype, int ndim, int N, int C, const int* in_size, const int* out_size,
                           const void* data, const void* grid, void* out, cudaStream_t st)

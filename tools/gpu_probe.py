@@ -105,9 +105,12 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
     C = 1
     data = torch.rand((n_theta, C, *size), device="cuda")
     gt = ops.forward(grid, Tr, tess, 50)
-    med, best = timeit(lambda: ops.interpolate_forward(data, gt, size))
     byts = n_theta * nP * (4 * ndim + 8 * C)
-    emit(kind="interp_fwd", cfg=name, ms=med, gbps_alg=byts / med / 1e6, points_per_s=pairs / med * 1e3)
+    for var in (0, 1, 2):
+        _lib.set_tuning("interp_variant", var)
+        med, best = timeit(lambda: ops.interpolate_forward(data, gt, size))
+        emit(kind="interp_fwd", cfg=name, variant=var, ms=med, gbps_alg=byts / med / 1e6, points_per_s=pairs / med * 1e3)
+    _lib.set_tuning("interp_variant", 0)
     g2 = torch.randn_like(data)
     med, best = timeit(lambda: ops.interpolate_backward(data, gt, g2, True, False))
     byts = n_theta * nP * (8 * ndim + 8 * C)
