@@ -37,7 +37,7 @@ template <> struct R<double> {
     static __device__ __forceinline__ double flo(double a) { return floor(a); }
 };
 
-int g_interp_variant = 0;   // experiment knob (cpab_b200_set_tuning "interp_variant")
+int g_interp_variant = 2;   // 0: 4 points in flight, 1 CTA/SM target; 1: 2 / 6; 2: 1 / 8 (default, measured best) (cpab_b200_set_tuning "interp_variant")
 
 struct Shape {
     int N, C;

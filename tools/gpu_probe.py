@@ -110,7 +110,7 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
         _lib.set_tuning("interp_variant", var)
         med, best = timeit(lambda: ops.interpolate_forward(data, gt, size))
         emit(kind="interp_fwd", cfg=name, variant=var, ms=med, gbps_alg=byts / med / 1e6, points_per_s=pairs / med * 1e3)
-    _lib.set_tuning("interp_variant", 0)
+    _lib.set_tuning("interp_variant", 2)
     g2 = torch.randn_like(data)
     med, best = timeit(lambda: ops.interpolate_backward(data, gt, g2, True, False))
     byts = n_theta * nP * (8 * ndim + 8 * C)
