@@ -117,13 +117,16 @@ CPAB_HD void divmod_exact(float p, float nf, float w, float& kf, float& r)
 CPAB_HD int find_cell_1d(float p0, const Geom& g)
 {
 #if defined(__CUDA_ARCH__)
-    const float s = __fmul_rn(p0, g.nf[0]);                 // the reference's float multiply, unfused
+    // the reference's float multiply, unfused, then floor-and-convert in ONE conversion-pipe
+    // instruction (cvt.rmi saturates, NaN -> 0) and an integer clamp: the 1-D loop is otherwise
+    // bound by the conversion pipe (FRND + F2I per step)
+    const int c = __float2int_rd(__fmul_rn(p0, g.nf[0]));
+    return min(max(c, 0), g.nc[0] - 1);
 #else
     const float s = p0 * g.nf[0];
-#endif
-    // floorf then clamp in float (NaN-safe through fminf/fmaxf), one conversion at the end
     const float c = fminf(fmaxf(floorf(s), 0.0f), g.nf[0] - 1.0f);
     return (int)c;
+#endif
 }
 
 CPAB_HD int find_cell_1d(double p0, const Geom& g)

@@ -240,21 +240,33 @@ k_interp_fwd(const T* __restrict__ data, const T* __restrict__ grid, T* __restri
     else interp_fwd_tile<T, NDIM, false, BATCH>(data, grid, out, s, sg);
 }
 
-// 1-D: no transposition needed
+// 1-D: no transposition needed.  A thread owns PT points (strided by the CTA width so that every
+// access stays unit-stride) and issues all their loads before blending.
+constexpr int PT1D = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_interp_fwd_1d(const T* __restrict__ data, const T* __restrict__ grid, T* __restrict__ out, Shape s)
 {
     const int n = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.O[0]) return;
-    int t0, t1;
-    T w[1];
-    taps(grid[(size_t)n * s.O[0] + i], s.S[0], t0, t1, w[0]);
+    const int i0 = blockIdx.x * (256 * PT1D) + threadIdx.x;
+    const T* gn = grid + (size_t)n * s.O[0];
+    T gc[PT1D];
+#pragma unroll
+    for (int u = 0; u < PT1D; ++u) gc[u] = (i0 + 256 * u < s.O[0]) ? gn[i0 + 256 * u] : (T)0;
+    int t0[PT1D], t1[PT1D];
+    T w[PT1D];
+#pragma unroll
+    for (int u = 0; u < PT1D; ++u) taps(gc[u], s.S[0], t0[u], t1[u], w[u]);
     for (int c = 0; c < s.C; ++c) {
         const T* dp = data + ((size_t)n * s.C + c) * s.S[0];
-        T v[2] = {__ldg(dp + t0), __ldg(dp + t1)};
-        out[((size_t)n * s.C + c) * s.O[0] + i] = blend<1>(v, w);
+        T v[PT1D][2];
+#pragma unroll
+        for (int u = 0; u < PT1D; ++u) { v[u][0] = __ldg(dp + t0[u]); v[u][1] = __ldg(dp + t1[u]); }
+        T* op = out + ((size_t)n * s.C + c) * s.O[0];
+#pragma unroll
+        for (int u = 0; u < PT1D; ++u)
+            if (i0 + 256 * u < s.O[0]) op[i0 + 256 * u] = blend<1>(v[u], &w[u]);
     }
 }
 
@@ -383,25 +395,42 @@ k_interp_bwd_1d(const T* __restrict__ data, const T* __restrict__ grid, const T*
                 T* __restrict__ dgrid, T* __restrict__ ddata, Shape s)
 {
     const int n = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.O[0]) return;
-    int t0, t1;
-    T w[1];
-    taps(grid[(size_t)n * s.O[0] + i], s.S[0], t0, t1, w[0]);
-    T dg = 0;
+    const int i0 = blockIdx.x * (256 * PT1D) + threadIdx.x;
+    const T* gn = grid + (size_t)n * s.O[0];
+    T gc[PT1D];
+#pragma unroll
+    for (int u = 0; u < PT1D; ++u) gc[u] = (i0 + 256 * u < s.O[0]) ? gn[i0 + 256 * u] : (T)0;
+    int t0[PT1D], t1[PT1D];
+    T w[PT1D], dg[PT1D];
+#pragma unroll
+    for (int u = 0; u < PT1D; ++u) { taps(gc[u], s.S[0], t0[u], t1[u], w[u]); dg[u] = 0; }
     for (int c = 0; c < s.C; ++c) {
         const size_t ch = (size_t)n * s.C + c;
         const T* dp = data + ch * s.S[0];
-        const T g = gout[ch * s.O[0] + i];
-        T v[2] = {__ldg(dp + t0), __ldg(dp + t1)}, gv[2], dw[1];
-        blend_vjp<1>(v, w, g, gv, dw);
-        dg += dw[0];
-        if (ddata != nullptr) {
-            atomicAdd(ddata + ch * s.S[0] + t0, gv[0]);
-            atomicAdd(ddata + ch * s.S[0] + t1, gv[1]);
+        const T* gp = gout + ch * s.O[0];
+        T v[PT1D][2], g[PT1D];
+#pragma unroll
+        for (int u = 0; u < PT1D; ++u) {
+            v[u][0] = __ldg(dp + t0[u]);
+            v[u][1] = __ldg(dp + t1[u]);
+            g[u] = (i0 + 256 * u < s.O[0]) ? gp[i0 + 256 * u] : (T)0;
+        }
+#pragma unroll
+        for (int u = 0; u < PT1D; ++u) {
+            T gv[2], dw[1];
+            blend_vjp<1>(v[u], &w[u], g[u], gv, dw);
+            dg[u] += dw[0];
+            if (ddata != nullptr && i0 + 256 * u < s.O[0]) {
+                atomicAdd(ddata + ch * s.S[0] + t0[u], gv[0]);
+                atomicAdd(ddata + ch * s.S[0] + t1[u], gv[1]);
+            }
         }
     }
-    if (dgrid != nullptr) dgrid[(size_t)n * s.O[0] + i] = dg * (T)(s.S[0] - 1);
+    if (dgrid != nullptr) {
+#pragma unroll
+        for (int u = 0; u < PT1D; ++u)
+            if (i0 + 256 * u < s.O[0]) dgrid[(size_t)n * s.O[0] + i0 + 256 * u] = dg[u] * (T)(s.S[0] - 1);
+    }
 }
 
 template <typename T>
@@ -411,7 +440,7 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
     if (s.N == 0 || s.C == 0) return kOk;
     for (int j = 0; j < ndim; ++j) if (s.O[j] == 0) return kOk;
     if (ndim == 1) {
-        dim3 g((unsigned)((s.O[0] + 255) / 256), (unsigned)s.N);
+        dim3 g((unsigned)((s.O[0] + 256 * PT1D - 1) / (256 * PT1D)), (unsigned)s.N);
         if (s.N > 65535) {   // grid.y limit: slab the batch
             for (int n0 = 0; n0 < s.N; n0 += 65535) {
                 Shape sub = s;
