@@ -22,6 +22,7 @@
 // coordinate.  The loop trip count is fixed (nstepsolver), so divergence is confined to the rare
 // exact paths of the cell search.
 #include <string_view>
+#include <type_traits>
 
 #include "cpab_common.cuh"
 
@@ -398,40 +399,45 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
 
             // ---- pass 1: the RK2 trajectory.  Records the cell of every step and a checkpoint
             //      of p at the start of every segment; the only pass that searches cells.
-            for (int sg = 0; sg < nseg; ++sg) {
+            //      (FULL = a whole segment that is not the last one: no bounds checks.)
+            auto pass1 = [&](int sg, auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
                 for (int j = 0; j < NDIM; ++j) ck[(sg * NDIM + j) * BLOCK + threadIdx.x] = p[j];
 #pragma unroll
                 for (int s = 0; s < SEG; ++s) {
                     const int n = sg * SEG + s;
-                    if (n < nsteps) {
+                    if (FULL || n < nsteps) {
                         const int c = find_cell<NDIM>(p, g);
                         if (wide) ct32[n * BLOCK + threadIdx.x] = c;
                         else ct16[n * BLOCK + threadIdx.x] = (unsigned short)c;
-                        if (n + 1 < nsteps) {
+                        if (FULL || n + 1 < nsteps) {
                             T a[PPC];
                             tab.load(c, a);
                             rk2_step<NDIM>(a, p, h, hh);
                         }
                     }
                 }
-            }
+            };
+            for (int sg = 0; sg + 1 < nseg; ++sg) pass1(sg, std::true_type{});
+            pass1(nseg - 1, std::false_type{});
 
             // ---- pass 2: segments in reverse; replay p into registers (no search), sweep back
-            for (int sg = nseg - 1; sg >= 0; --sg) {
-                const int len = (nsteps - sg * SEG) < SEG ? (nsteps - sg * SEG) : SEG;
+            auto pass2 = [&](int sg, auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                const int len = FULL ? SEG : nsteps - sg * SEG;
                 T ps[SEG][NDIM];
                 int cs[SEG];
 #pragma unroll
                 for (int j = 0; j < NDIM; ++j) p[j] = ck[(sg * NDIM + j) * BLOCK + threadIdx.x];
 #pragma unroll
                 for (int s = 0; s < SEG; ++s) {
-                    if (s < len) {
+                    if (FULL || s < len) {
                         const int n = sg * SEG + s;
                         cs[s] = wide ? ct32[n * BLOCK + threadIdx.x] : (int)ct16[n * BLOCK + threadIdx.x];
 #pragma unroll
                         for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
-                        if (s + 1 < len) {
+                        if (s + 1 < SEG && (FULL || s + 1 < len)) {
                             T a[PPC];
                             tab.load(cs[s], a);
                             rk2_step<NDIM>(a, p, h, hh);
@@ -440,22 +446,11 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
                 }
 #pragma unroll
                 for (int s = SEG - 1; s >= 0; --s) {
-                    if (s < len) {
+                    if (FULL || s < len) {
                         const int c = cs[s];
-                        T a[PPC], v[NDIM], pm[NDIM], w[NDIM];
+                        T a[PPC];
                         tab.load(c, a);
-                        affine_fma<NDIM>(a, ps[s], v);
-#pragma unroll
-                        for (int j = 0; j < NDIM; ++j) pm[j] = Num<T>::fma(hh, v[j], ps[s][j]);
-                        // w = A_lin^T lambda
-#pragma unroll
-                        for (int r = 0; r < NDIM; ++r) {
-                            T t = a[r] * lam[0];
-#pragma unroll
-                            for (int j = 1; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], lam[j], t);
-                            w[r] = t;
-                        }
-                        if (c != cur) {                 // left a cell: hand its sum to G[theta]
+                        if (c != cur) {                 // left a cell: hand its sum to R[theta]
                             if (cur >= 0) {
 #pragma unroll
                                 for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gg + (size_t)cur * PPC + e, acc[e]);
@@ -464,26 +459,35 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
                             for (int e = 0; e < PPC; ++e) acc[e] = 0;
                             cur = c;
                         }
+                        // R_c += lambda_{n+1} [p_n;1]^T
 #pragma unroll
                         for (int r = 0; r < NDIM; ++r) {
-                            const T hl = h * lam[r], hw = h2 * w[r];
 #pragma unroll
                             for (int cc = 0; cc < NDIM; ++cc)
-                                acc[r * (NDIM + 1) + cc] =
-                                    Num<T>::fma(hl, pm[cc], Num<T>::fma(hw, ps[s][cc], acc[r * (NDIM + 1) + cc]));
-                            acc[r * (NDIM + 1) + NDIM] += hl + hw;
+                                acc[r * (NDIM + 1) + cc] = Num<T>::fma(lam[r], ps[s][cc], acc[r * (NDIM + 1) + cc]);
+                            acc[r * (NDIM + 1) + NDIM] += lam[r];
                         }
-                        // lambda <- lambda + h w + (h^2/2) A_lin^T w
+                        // lambda_n = M^T lambda_{n+1} = lambda + L^T (h lambda + (h^2/2) L^T lambda)
+                        T u[NDIM];
 #pragma unroll
                         for (int r = 0; r < NDIM; ++r) {
-                            T t = a[r] * w[0];
+                            T t = a[r] * lam[0];
 #pragma unroll
-                            for (int j = 1; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], w[j], t);
-                            lam[r] = Num<T>::fma(h2, t, Num<T>::fma(h, w[r], lam[r]));
+                            for (int j = 1; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], lam[j], t);
+                            u[r] = Num<T>::fma(h2, t, h * lam[r]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < NDIM; ++r) {
+                            T t = lam[r];
+#pragma unroll
+                            for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], u[j], t);
+                            lam[r] = t;
                         }
                     }
                 }
-            }
+            };
+            pass2(nseg - 1, std::false_type{});
+            for (int sg = nseg - 2; sg >= 0; --sg) pass2(sg, std::true_type{});
             if (dpoints != nullptr) {
                 T* dp = dpoints + (size_t)theta * NDIM * nP;
 #pragma unroll
@@ -492,6 +496,39 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
         }
         flush_runs<T, PPC>(Gg, cur, acc);
     }
+}
+
+// R -> G, per (theta, cell), in place:  G_c = h R_c + (h^2/2) (R_c Atilde^T + L^T R_c),
+// Atilde = [[L, t], [0, 0]].  (sum over the steps spent in cell c of
+// h lambda [pMid;1]^T + (h^2/2) (L^T lambda) [p;1]^T with [pMid;1] = (I + (h/2) Atilde) [p;1].)
+template <typename T, int NDIM>
+__global__ void __launch_bounds__(256)
+k_r_to_g(T* __restrict__ RG, const T* __restrict__ As, long n_blocks, int nsteps)
+{
+    constexpr int PPC = Dim<NDIM>::kPpc;
+    constexpr int M = NDIM + 1;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    T R[PPC], A[PPC], Gc[PPC];
+#pragma unroll
+    for (int e = 0; e < PPC; ++e) { R[e] = RG[i * PPC + e]; A[e] = As[i * PPC + e]; }
+    const T h = (T)(1.0 / nsteps), h2 = (T)(0.5 / nsteps / nsteps);
+#pragma unroll
+    for (int r = 0; r < NDIM; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < M; ++cc) {
+            T t = 0;
+            if (cc < NDIM) {                                   // (R Atilde^T)[r][cc] = sum_k R[r][k] A[cc][k]
+#pragma unroll
+                for (int k = 0; k < M; ++k) t = Num<T>::fma(R[r * M + k], A[cc * M + k], t);
+            }
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(A[j * M + r], R[j * M + cc], t);   // (L^T R)[r][cc]
+            Gc[r * M + cc] = Num<T>::fma(h2, t, h * R[r * M + cc]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < PPC; ++e) RG[i * PPC + e] = Gc[e];
 }
 
 // dtheta[t][k] = sum_e G[t][e] * B[e][k]      (G [n_theta,D], B [D,d] row-major, dtheta [n_theta,d])
@@ -713,6 +750,12 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
     if (!fits) {
         set_error("backward: nstepsolver=%d needs more checkpoint memory than one CTA has", nsteps);
         return kErrUnsupported;
+    }
+    {
+        const long n_blocks = (long)n_theta * g.n_cells;
+        k_r_to_g<T, NDIM><<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>((T*)ws, (const T*)As, n_blocks, nsteps);
+        CPAB_CUDA_OK(cudaGetLastError());
+        count_launch();
     }
     constexpr int TT = 8;
     dim3 grid((unsigned)((n_theta + TT - 1) / TT), (unsigned)((d + 127) / 128));
