@@ -51,6 +51,10 @@ WORKLOADS = {
     "cfg3_2d_t10x10vp_b512_512x512": ([10, 10], 512, [512, 512], 1, {"volume_perservation": True}),
     "cfg4_3d_t4x4x4_b16_128cubed": ([4, 4, 4], 16, [128, 128, 128], 1, {}),
     "cfg5_1d_t100_b8192_1024": ([100], 8192, [1024], 1, {}),
+    # BASELINE configs[4]: CpabSequential of 4 warps, alignment mode -- every series has its own
+    # thetas (local gradients) and all series are pulled towards ONE shared, learnable template
+    # whose gradient is summed over the theta-shards with an NCCL all-reduce (the only collective)
+    "cfg5_1d_seq4_alignment_b8192_1024": ([100], 8192, [1024], 1, {"sequential": 4}),
 }
 DEFAULT_WORKLOAD = "cfg2_2d_t3x3_b64_256x256"
 
@@ -212,7 +216,12 @@ def run_gpu_arm(args):
     nP = int(np.prod(outsize))
     pairs_rank = n_theta * nP
     torch.manual_seed(1234 + 2 + rank)
+    kw = dict(kw)
+    n_warps = kw.pop("sequential", 0)
     T = Cpab(tess, backend="pytorch", device="gpu", **kw)
+    if n_warps:
+        run_alignment_arm(args, T, n_warps, tess, n_theta, outsize, C, rank, world, dev)
+        return
     theta_h = torch.randn(n_theta, T.params.d).pin_memory()
     data_h = torch.rand(n_theta, C, *outsize).pin_memory()
     R = torch.randn(n_theta, C, *outsize, device=dev)
@@ -364,6 +373,95 @@ def run_gpu_arm(args):
         "build": lib.cpab_b200_build_info().decode(),
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_alignment_arm(args, T0, n_warps, tess, n_theta, outsize, C, rank, world, dev):
+    """CpabSequential alignment step: forward through n_warps chained flows + interpolation,
+    loss against a shared template, backward to every warp's thetas (points_grad extension) and
+    to the template, NCCL all-reduce of the template gradient.  pairs = n_warps * n_theta * nP."""
+    import torch
+    import torch.distributed as dist
+    from libcpab_b200 import Cpab, CpabSequential, _lib
+    from libcpab_b200.distributed import allreduce_grad_
+    Ts = [T0] + [Cpab(tess, backend="pytorch", device="gpu", basis=T0.params.basis) for _ in range(n_warps - 1)]
+    for t in Ts:
+        t.params.points_grad = True
+    S = CpabSequential(*Ts)
+    nP = int(np.prod(outsize))
+    pairs_rank = n_warps * n_theta * nP
+    thetas_h = [(0.5 * torch.randn(n_theta, T0.params.d)).pin_memory() for _ in range(n_warps)]
+    data_h = torch.rand(n_theta, C, *outsize).pin_memory()
+    thetas = [t.to(dev).requires_grad_(True) for t in thetas_h]
+    data = data_h.to(dev)
+    template = torch.rand(1, C, *outsize, device=dev).requires_grad_(True)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    grads_h = [torch.empty(n_theta, T0.params.d).pin_memory() for _ in range(n_warps)]
+
+    def step(ths, da):
+        for t in ths:
+            t.grad = None
+        template.grad = None
+        out = S.transform_data(da, ths, outsize)
+        loss = (out - template).square().sum()
+        loss.backward()
+        allreduce_grad_(template)
+        return loss
+
+    def step_resident():
+        step(thetas, data)
+
+    def step_e2e():
+        ths = [t.to(dev, non_blocking=True).requires_grad_(True) for t in thetas_h]
+        da = data_h.to(dev, non_blocking=True)
+        step(ths, da)
+        for g, t in zip(grads_h, ths):
+            g.copy_(t.grad, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in evs:
+            flush.add_(1.0)
+            a.record(); fn(); b.record()
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident(); step_e2e()
+    l0 = _lib.launch_count()
+    _lib.profile_enable(True)
+    total_ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - l0
+    prof = {k: _lib.profile_read(k) for k in _lib.PROFILE_SLOTS}
+    _lib.profile_enable(False)
+    e2e_ms = timed(step_e2e, args.steps)
+    if rank == 0:
+        line = {
+            "metric": "pairs_per_s_fwd_bwd", "value": pairs_rank * world / (total_ms / args.steps * 1e-3),
+            "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "tess_size": tess, "n_theta_per_gpu": n_theta, "outsize": outsize,
+                       "warps": n_warps, "step": "CpabSequential.transform_data fwd + bwd to all thetas and a shared template",
+                       "collective": "NCCL all-reduce of the shared template gradient (%d floats)" % template.numel(),
+                       "l2": "flushed before every timed step", "parallelism": f"theta-sharded x{world}"},
+            "e2e": {"value": pairs_rank * world / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(sum(t.numel() for t in thetas_h) * 4 + data_h.numel() * 4),
+                    "d2h_bytes_per_step": int(sum(g.numel() for g in grads_h) * 4)},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+        }
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

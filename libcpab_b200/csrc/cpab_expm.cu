@@ -146,50 +146,71 @@ template <int M> __device__ __forceinline__ Mat<M> expm_pade13(Mat<M> A)
 }
 
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NDIM>
+// One thread owns one cell for TT consecutive thetas: every basis row fetched from L2 is reused
+// TT times from registers (the contraction is a skinny GEMM; for 65536 thetas of a 1-D [100]
+// tessellation the un-tiled version re-read the 79 KB basis 65536 times).
+template <typename T, int NDIM, int TT>
 __global__ void __launch_bounds__(128)
 k_theta_to_trels(const T* __restrict__ basis_t, const T* __restrict__ theta, T* __restrict__ As,
-                 T* __restrict__ trels, int n_cells, int d, int nsteps)
+                 T* __restrict__ trels, int n_cells, int d, int nsteps, int n_theta)
 {
     constexpr int PPC = Dim<NDIM>::kPpc;
     constexpr int M = NDIM + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sth = reinterpret_cast<T*>(smem_raw);
-    const int t = blockIdx.y;
+    T* sth = reinterpret_cast<T*>(smem_raw);                    // [TT][d]
+    const int t0 = blockIdx.y * TT;
     const int D = n_cells * PPC;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) sth[j] = theta[(size_t)t * d + j];
+    for (int x = threadIdx.x; x < TT * d; x += blockDim.x) {
+        const int u = x / d, j = x - u * d;
+        sth[x] = (t0 + u < n_theta) ? theta[(size_t)(t0 + u) * d + j] : (T)0;
+    }
     __syncthreads();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
 
-    T acc[PPC];
+    T acc[TT][PPC];
 #pragma unroll
-    for (int e = 0; e < PPC; ++e) acc[e] = 0;
+    for (int u = 0; u < TT; ++u)
+#pragma unroll
+        for (int e = 0; e < PPC; ++e) acc[u][e] = 0;
     const T* col = basis_t + (size_t)c * PPC;
     for (int j = 0; j < d; ++j) {
-        const T th = sth[j];
         const T* row = col + (size_t)j * D;
+        T b[PPC];
 #pragma unroll
-        for (int e = 0; e < PPC; ++e) acc[e] = fma(__ldg(row + e), th, acc[e]);
+        for (int e = 0; e < PPC; ++e) b[e] = __ldg(row + e);
+#pragma unroll
+        for (int u = 0; u < TT; ++u) {
+            const T th = sth[u * d + j];
+#pragma unroll
+            for (int e = 0; e < PPC; ++e) acc[u][e] = fma(b[e], th, acc[u][e]);
+        }
     }
-    T* Aout = As + ((size_t)t * n_cells + c) * PPC;
-#pragma unroll
-    for (int e = 0; e < PPC; ++e) Aout[e] = acc[e];
-
-    // dT * A in the working precision (as the reference: `dT*AsSquare` on a float32 tensor),
-    // then the exponential in double
     const T dT = (T)(1.0 / nsteps);
-    Mat<M> X;
+#pragma unroll 1
+    for (int u = 0; u < TT; ++u) {
+        if (t0 + u >= n_theta) break;
+        T* Aout = As + ((size_t)(t0 + u) * n_cells + c) * PPC;
+        // dT * A in the working precision (as the reference: `dT*AsSquare` on a float32 tensor),
+        // then the exponential in double
+        Mat<M> X;
 #pragma unroll
-    for (int i = 0; i < M; ++i)
+        for (int e = 0; e < PPC; ++e) {
+            T v = acc[0][e];
 #pragma unroll
-        for (int j = 0; j < M; ++j) X.a[i][j] = i < NDIM ? (double)(T)(dT * acc[i * M + j]) : 0.0;
-    const Mat<M> E = expm_pade13<M>(X);
-    T* Tout = trels + ((size_t)t * n_cells + c) * PPC;
+            for (int q = 1; q < TT; ++q) v = (u == q) ? acc[q][e] : v;      // keeps acc in registers
+            Aout[e] = v;
+            X.a[e / M][e % M] = (double)(T)(dT * v);
+        }
 #pragma unroll
-    for (int i = 0; i < NDIM; ++i)
+        for (int j = 0; j < M; ++j) X.a[NDIM][j] = 0.0;
+        const Mat<M> E = expm_pade13<M>(X);
+        T* Tout = trels + ((size_t)(t0 + u) * n_cells + c) * PPC;
 #pragma unroll
-        for (int j = 0; j < M; ++j) Tout[i * M + j] = (T)E.a[i][j];
+        for (int i = 0; i < NDIM; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) Tout[i * M + j] = (T)E.a[i][j];
+    }
 }
 
 // standalone batched expm of [n, M, M] (tests; and the reference's expm() as an op)
@@ -214,10 +235,13 @@ template <typename T, int NDIM>
 int theta_to_trels_t(const Geom& g, int nsteps, int n_theta, int d, const void* basis_t,
                      const void* theta, void* As, void* trels, cudaStream_t st)
 {
-    if (n_theta > 65535) {
-        // grid.y limit: process in slabs of 65535 thetas
-        for (int t0 = 0; t0 < n_theta; t0 += 65535) {
-            const int n = n_theta - t0 < 65535 ? n_theta - t0 : 65535;
+    constexpr int TT = NDIM == 1 ? 16 : (NDIM == 2 ? 8 : 4);
+    const long ty = (n_theta + TT - 1) / TT;
+    if (ty > 65535) {
+        // grid.y limit: process in slabs
+        const int slab = 65535 * TT;
+        for (int t0 = 0; t0 < n_theta; t0 += slab) {
+            const int n = n_theta - t0 < slab ? n_theta - t0 : slab;
             const size_t off = (size_t)t0 * g.n_cells * Dim<NDIM>::kPpc;
             int rc = theta_to_trels_t<T, NDIM>(g, nsteps, n, d, basis_t, (const T*)theta + (size_t)t0 * d,
                                                (T*)As + off, (T*)trels + off, st);
@@ -225,12 +249,12 @@ int theta_to_trels_t(const Geom& g, int nsteps, int n_theta, int d, const void* 
         }
         return kOk;
     }
-    dim3 grid((unsigned)((g.n_cells + 127) / 128), (unsigned)n_theta);
-    const size_t smem = (size_t)d * sizeof(T);
+    dim3 grid((unsigned)((g.n_cells + 127) / 128), (unsigned)ty);
+    const size_t smem = (size_t)TT * d * sizeof(T);
     if (smem > 48 * 1024) { set_error("theta dimension %d too large", d); return kErrUnsupported; }
     prof_begin(kProfThetaToTrels, st);
-    k_theta_to_trels<T, NDIM><<<grid, 128, smem, st>>>((const T*)basis_t, (const T*)theta, (T*)As,
-                                                        (T*)trels, g.n_cells, d, nsteps);
+    k_theta_to_trels<T, NDIM, TT><<<grid, 128, smem, st>>>((const T*)basis_t, (const T*)theta, (T*)As,
+                                                            (T*)trels, g.n_cells, d, nsteps, n_theta);
     prof_end(kProfThetaToTrels, st);
     count_launch();
     CPAB_CUDA_OK(cudaGetLastError());

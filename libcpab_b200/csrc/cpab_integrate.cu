@@ -28,7 +28,16 @@
 
 // -DCPAB_FAST_BUILD instantiates only the float32 2-D kernels (SASS experiments; never shipped).
 #ifdef CPAB_FAST_BUILD
+#ifndef CPAB_FAST_DIM
+#define CPAB_FAST_DIM 2
+#endif
+#if CPAB_FAST_DIM == 1
+#define CPAB_DISPATCH(T1D, T2D, T3D) (T1D)
+#elif CPAB_FAST_DIM == 2
 #define CPAB_DISPATCH(T1D, T2D, T3D) (T2D)
+#else
+#define CPAB_DISPATCH(T1D, T2D, T3D) (T3D)
+#endif
 #define CPAB_DTYPE(F, D) (F)
 #else
 #define CPAB_DISPATCH(T1D, T2D, T3D) (g.ndim == 1 ? (T1D) : g.ndim == 2 ? (T2D) : (T3D))
@@ -344,9 +353,9 @@ __device__ __forceinline__ void flush_runs(T* __restrict__ Gg, int key, T* acc)
     }
 }
 
-// resident CTAs per SM the register allocation is tuned for (float: ~80 regs in 1-D/2-D, ~100 in 3-D)
+// resident CTAs per SM the register allocation is tuned for (float: 80 regs in 1-D/2-D, 128 in 3-D -- fewer registers spill)
 template <typename T, int NDIM, int BLOCK> struct BwdOcc {
-    static constexpr int kMinBlocks = sizeof(T) == 8 ? 1 : 65536 / (BLOCK * (NDIM == 3 ? 102 : 80));
+    static constexpr int kMinBlocks = sizeof(T) == 8 ? 1 : 65536 / (BLOCK * (NDIM == 3 ? 128 : 80));
 };
 
 template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
@@ -571,6 +580,7 @@ k_grad_epilogue(const T* __restrict__ G, const T* __restrict__ B, T* __restrict_
 // host launchers
 // =====================================================================================================
 static int g_tune_fwd_ppt = 1;        // points advanced concurrently per thread in k_forward
+static int g_tune_chunk_auto = 0;     // 1: choose the chunk so that the grid fills whole waves
 static int g_tune_chunk_pts = 2048;   // points of one theta handled by one CTA
 static int g_tune_bwd_seg = 5;        // checkpoint spacing of k_backward
 static int g_tune_bwd_block = 128;
@@ -579,10 +589,11 @@ int set_tuning(const char* key, int value)
 {
     const std::string_view k(key);
     if (k == "fwd_ppt" && (value == 1 || value == 2)) { g_tune_fwd_ppt = value; return kOk; }
-    if (k == "chunk_pts" && value >= 256 && value % 256 == 0) { g_tune_chunk_pts = value; return kOk; }
+    if (k == "chunk_pts" && value >= 256 && value % 256 == 0) { g_tune_chunk_pts = value; g_tune_chunk_auto = 0; return kOk; }
+    if (k == "chunk_auto" && (value == 0 || value == 1)) { g_tune_chunk_auto = value; return kOk; }
     if (k == "bwd_seg" && (value == 5 || value == 10)) { g_tune_bwd_seg = value; return kOk; }
     if (k == "bwd_block" && (value == 64 || value == 128 || value == 256)) { g_tune_bwd_block = value; return kOk; }
-    if (k == "interp_variant" && value >= 0 && value <= 2) { set_interp_variant(value); return kOk; }
+    if (k == "interp_variant" && value >= 0 && value <= 4) { set_interp_variant(value); return kOk; }
     set_error("unknown tuning key/value %s=%d", key, value);
     return kErrArgument;
 }
@@ -605,10 +616,36 @@ int launch_findcellidx(int dtype, const Geom& g, const void* points, long nP, in
 #undef GO
 }
 
-static void pick_chunks(long nP, int& chunks, int& chunk_pts)
+static int sm_count()
 {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// Points of one theta handled by one CTA.  The grid is n_theta x chunks CTAs of equal work; with
+// `slots` CTAs resident on the chip the kernel takes ceil(grid/slots) waves, so among the
+// candidate chunk sizes pick the one minimising waves x (chunk + per-CTA staging overhead).
+// For large problems every candidate is within a percent and the default wins.
+static void pick_chunks(long nP, int n_theta, int block, int ctas_per_sm, int stage_cost, int& chunks, int& chunk_pts)
+{
+    const int unit = block > 256 ? block : 256;
     chunk_pts = g_tune_chunk_pts;
-    if (nP < chunk_pts) chunk_pts = (int)((nP + 255) / 256 * 256);
+    if (g_tune_chunk_auto && ctas_per_sm > 0) {
+        const long slots = (long)sm_count() * ctas_per_sm;
+        double best = 1e300;
+        for (int c = 1024; c <= 4096; c += unit) {
+            const long per_theta = (nP + c - 1) / c;
+            const long waves = ((long)n_theta * per_theta + slots - 1) / slots;
+            const double cost = (double)waves * (c + stage_cost) * (c == g_tune_chunk_pts ? 0.999 : 1.0);
+            if (cost < best) { best = cost; chunk_pts = c; }
+        }
+    }
+    if (nP < chunk_pts) chunk_pts = (int)((nP + unit - 1) / unit * unit);
     chunks = (int)((nP + chunk_pts - 1) / chunk_pts);
 }
 
@@ -616,12 +653,13 @@ template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT>
 static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int broadcast,
                           const void* points, const void* trels, void* out, cudaStream_t st)
 {
-    int chunks, chunk_pts;
-    pick_chunks(nP, chunks, chunk_pts);
     const size_t smem = SMEM ? (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T) : 0;
     auto kern = k_forward<T, NDIM, STRICT, SMEM, PPT>;
     if (smem > 48 * 1024)
         CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int chunks, chunk_pts, per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    pick_chunks(nP, n_theta, 256, per_sm, 512 + (int)(smem / 64), chunks, chunk_pts);
     const long long blocks = (long long)n_theta * chunks;
     if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
     prof_begin(kProfForward, st);
@@ -697,8 +735,6 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
                            const void* points, const void* As, const void* gout, void* G,
                            void* dpoints, cudaStream_t st, bool& fits)
 {
-    int chunks, chunk_pts;
-    pick_chunks(nP, chunks, chunk_pts);
     const int nseg = (nsteps + SEG - 1) / SEG;
     const size_t tbytes = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
     const size_t smem = (SMEM ? tbytes : 0) + (size_t)nseg * NDIM * BLOCK * sizeof(T) +
@@ -708,6 +744,9 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
     auto kern = k_backward<T, NDIM, SEG, SMEM, BLOCK>;
     if (smem > 48 * 1024)
         CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int chunks, chunk_pts, per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
+    pick_chunks(nP, n_theta, BLOCK, per_sm, 1024 + (int)(tbytes / 64), chunks, chunk_pts);
     const long long blocks = (long long)n_theta * chunks;
     if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
     prof_begin(kProfBackward, st);

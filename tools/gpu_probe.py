@@ -72,6 +72,9 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
                  tflops_alg=pairs * F_FWD[ndim] / med / 1e9, frac_fp32=pairs * F_FWD[ndim] / med / 1e9 / peak, **extra)
 
     fwd_line("default")
+    _lib.set_tuning("chunk_auto", 1)
+    fwd_line("chunk_auto")
+    _lib.set_tuning("chunk_auto", 0)
     if variants:
         for ppt in (1, 2):
             for chunk in (1024, 4096):
@@ -89,6 +92,13 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
              tflops_alg=pairs * F_BWD[ndim] / med / 1e9, frac_fp32=pairs * F_BWD[ndim] / med / 1e9 / peak)
 
     bwd_line("default")
+    _lib.set_tuning("chunk_auto", 1)
+    bwd_line("chunk_auto")
+    _lib.set_tuning("chunk_auto", 0)
+    for chunk in (1536, 2816, 4096):
+        _lib.set_tuning("chunk_pts", chunk)
+        bwd_line(f"chunk{chunk}")
+    _lib.set_tuning("chunk_pts", 2048)
     if variants:
         for seg in (5, 10):
             for block in (64, 128, 256):
@@ -106,7 +116,7 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
     data = torch.rand((n_theta, C, *size), device="cuda")
     gt = ops.forward(grid, Tr, tess, 50)
     byts = n_theta * nP * (4 * ndim + 8 * C)
-    for var in (0, 1, 2):
+    for var in (0, 1, 2, 3, 4):
         _lib.set_tuning("interp_variant", var)
         med, best = timeit(lambda: ops.interpolate_forward(data, gt, size))
         emit(kind="interp_fwd", cfg=name, variant=var, ms=med, gbps_alg=byts / med / 1e6, points_per_s=pairs / med * 1e3)
