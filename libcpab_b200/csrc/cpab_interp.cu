@@ -195,13 +195,15 @@ __device__ __forceinline__ void interp_fwd_tile(const T* __restrict__ data, cons
     }
     __syncthreads();
 
-    // phase B: a warp runs along the last index; BATCH points per thread are in flight at a time
+    // phase B: a warp runs along the last index; BATCH points per thread are in flight at a time.
+    // Pointers advance by one channel plane per iteration; everything else is a 32-bit offset.
     const int iF = f0 + lane;
     const int plane = s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
     const T* dn = data + (size_t)n * s.C * plane;
     T* on = out + (size_t)n * s.C * nP + (NDIM == 2 ? (a0 + wrp) * s.O[1] + iF
                                                       : ((a0 + wrp) * s.O[1] + im) * s.O[2] + iF);
     const int ostride = 8 * (NDIM == 2 ? s.O[1] : s.O[1] * s.O[2]);     // output stride of one rep
+    const int nch = s.C;
 #pragma unroll
     for (int r0 = 0; r0 < REPS; r0 += BATCH) {
         Taps<T, NDIM> tp[BATCH];
@@ -215,15 +217,17 @@ __device__ __forceinline__ void interp_fwd_tile(const T* __restrict__ data, cons
             for (int j = 0; j < NDIM; ++j) gc[j] = sg[j][lane][a];
             tp[b] = make_taps<T, NDIM>(gc, s);
         }
-        for (int c = 0; c < s.C; ++c) {
-            const T* dp = dn + (size_t)c * plane;
+        const T* dp = dn;
+        T* op = on + r0 * ostride;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c, dp += plane, op += nP) {
             T v[BATCH][NC];
 #pragma unroll
             for (int b = 0; b < BATCH; ++b)
                 if (FULL || ok[b]) gather<T, NDIM>(dp, tp[b], v[b]);
 #pragma unroll
             for (int b = 0; b < BATCH; ++b)
-                if (FULL || ok[b]) on[(size_t)c * nP + (r0 + b) * ostride] = blend<NDIM>(v[b], tp[b].w);
+                if (FULL || ok[b]) op[b * ostride] = blend<NDIM>(v[b], tp[b].w);
         }
     }
 }
@@ -238,93 +242,6 @@ k_interp_fwd(const T* __restrict__ data, const T* __restrict__ grid, T* __restri
     const bool full = (blockIdx.x * TILE + TILE <= s.O[0]) && (blockIdx.y * TILE + TILE <= s.O[NDIM - 1]);
     if (full) interp_fwd_tile<T, NDIM, true, BATCH>(data, grid, out, s, sg);
     else interp_fwd_tile<T, NDIM, false, BATCH>(data, grid, out, s, sg);
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward, software-pipelined: a CTA walks a strip of STRIP tiles along the first index; the grid
-// tile of step t+1 is fetched with cp.async (global -> shared, no registers) while the texels of
-// tile t are gathered and blended, so the two dependent memory round trips of a tile overlap
-// across tiles.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool pred)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const int n = pred ? 4 : 0;                                   // 0 bytes read => zero fill
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <typename T, int NDIM, int BATCH, int STRIP, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k_interp_fwd_pipe(const T* __restrict__ data, const T* __restrict__ grid, T* __restrict__ out, Shape s)
-{
-    static_assert(sizeof(T) == 4, "cp.async path is float32 only");
-    constexpr int NC = 1 << NDIM;
-    __shared__ T sg[2][NDIM][TILE][TILE + 1];
-    const int mid = NDIM == 3 ? s.O[1] : 1;
-    const int n = blockIdx.z / mid, im = blockIdx.z - n * mid;
-    const int f0 = blockIdx.y * TILE;
-    const int O0 = s.O[0], OF = s.O[NDIM - 1];
-    const int nP = O0 * (NDIM >= 2 ? s.O[1] : 1) * (NDIM >= 3 ? s.O[2] : 1);
-    const int pstride = NDIM == 2 ? O0 : O0 * s.O[1];
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const int tiles_x = (O0 + TILE - 1) / TILE;
-    const int tx0 = blockIdx.x * STRIP;
-    const int tx1 = tx0 + STRIP < tiles_x ? tx0 + STRIP : tiles_x;
-    const T* gbase = grid + (size_t)n * NDIM * nP + (NDIM == 3 ? O0 * im : 0) + pstride * (f0 + wrp);
-    const int plane = s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
-    const T* dn = data + (size_t)n * s.C * plane;
-    const int iF = f0 + lane;
-    const int ostride = 8 * (NDIM == 2 ? s.O[1] : s.O[1] * s.O[2]);
-
-    auto fetch = [&](int tx, int buf) {
-        const int i0 = tx * TILE + lane;
-#pragma unroll
-        for (int rep = 0; rep < REPS; ++rep) {
-            const bool ok = (i0 < O0) && (f0 + wrp + 8 * rep < OF);
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j)
-                cp_async4(&sg[buf][j][wrp + 8 * rep][lane], gbase + (ok ? j * nP + i0 + rep * 8 * pstride : 0), ok);
-        }
-        cp_async_commit();
-    };
-
-    fetch(tx0, 0);
-    for (int tx = tx0; tx < tx1; ++tx) {
-        const int buf = (tx - tx0) & 1;
-        if (tx + 1 < tx1) { fetch(tx + 1, buf ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
-        const int a0 = tx * TILE;
-        T* on = out + (size_t)n * s.C * nP + (NDIM == 2 ? (a0 + wrp) * s.O[1] + iF
-                                                          : ((a0 + wrp) * s.O[1] + im) * s.O[2] + iF);
-#pragma unroll
-        for (int r0 = 0; r0 < REPS; r0 += BATCH) {
-            Taps<T, NDIM> tp[BATCH];
-            bool ok[BATCH];
-#pragma unroll
-            for (int b = 0; b < BATCH; ++b) {
-                const int a = wrp + 8 * (r0 + b);
-                ok[b] = (a0 + a < O0 && iF < OF);
-                T gc[NDIM];
-#pragma unroll
-                for (int j = 0; j < NDIM; ++j) gc[j] = sg[buf][j][lane][a];
-                tp[b] = make_taps<T, NDIM>(gc, s);
-            }
-            for (int c = 0; c < s.C; ++c) {
-                const T* dp = dn + (size_t)c * plane;
-                T v[BATCH][NC];
-#pragma unroll
-                for (int b = 0; b < BATCH; ++b)
-                    if (ok[b]) gather<T, NDIM>(dp, tp[b], v[b]);
-#pragma unroll
-                for (int b = 0; b < BATCH; ++b)
-                    if (ok[b]) on[(size_t)c * nP + (r0 + b) * ostride] = blend<NDIM>(v[b], tp[b].w);
-            }
-        }
-        __syncthreads();
-    }
 }
 
 // 1-D: no transposition needed.  A thread owns PT points (strided by the CTA width so that every
@@ -362,7 +279,7 @@ k_interp_fwd_1d(const T* __restrict__ data, const T* __restrict__ grid, T* __res
 // into a zero-initialised buffer).  Same tiling as the forward; the d/dgrid tile returns through
 // shared memory so that it is stored unit-stride along the first index.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NDIM, bool FULL, bool DDATA>
+template <typename T, int NDIM, bool FULL, bool DDATA, int BATCH>
 __device__ __forceinline__ void interp_bwd_tile(const T* __restrict__ data, const T* __restrict__ grid,
                                                 const T* __restrict__ gout, T* __restrict__ dgrid,
                                                 T* __restrict__ ddata, const Shape& s,
@@ -402,44 +319,51 @@ __device__ __forceinline__ void interp_bwd_tile(const T* __restrict__ data, cons
     const T* gon = gout + (size_t)n * s.C * nP + (NDIM == 2 ? (a0 + wrp) * s.O[1] + iF
                                                              : ((a0 + wrp) * s.O[1] + im) * s.O[2] + iF);
     const int ostride = 8 * (NDIM == 2 ? s.O[1] : s.O[1] * s.O[2]);
-    Taps<T, NDIM> tp[REPS];
-    bool ok[REPS];
+    const int nch = s.C;
     T dg[REPS][NDIM];
 #pragma unroll
-    for (int rep = 0; rep < REPS; ++rep) {
-        const int a = wrp + 8 * rep;
-        ok[rep] = FULL || (a0 + a < O0 && iF < OF);
-        T gc[NDIM];
+    for (int r0 = 0; r0 < REPS; r0 += BATCH) {
+        Taps<T, NDIM> tp[BATCH];
+        bool ok[BATCH];
 #pragma unroll
-        for (int j = 0; j < NDIM; ++j) { gc[j] = sg[j][lane][a]; dg[rep][j] = 0; }
-        tp[rep] = make_taps<T, NDIM>(gc, s);
-    }
-    for (int c = 0; c < s.C; ++c) {
-        const T* dp = dn + (size_t)c * plane;
-        T v[REPS][NC], g[REPS];
+        for (int b = 0; b < BATCH; ++b) {
+            const int a = wrp + 8 * (r0 + b);
+            ok[b] = FULL || (a0 + a < O0 && iF < OF);
+            T gc[NDIM];
 #pragma unroll
-        for (int rep = 0; rep < REPS; ++rep) {
-            if (FULL || ok[rep]) {
-                gather<T, NDIM>(dp, tp[rep], v[rep]);
-                g[rep] = gon[(size_t)c * nP + rep * ostride];
-            }
+            for (int j = 0; j < NDIM; ++j) { gc[j] = sg[j][lane][a]; dg[r0 + b][j] = 0; }
+            tp[b] = make_taps<T, NDIM>(gc, s);
         }
+        const T* dp = dn;
+        const T* gp = gon + r0 * ostride;
+        T* qd = ddn;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c, dp += plane, gp += nP) {
+            T v[BATCH][NC], g[BATCH];
 #pragma unroll
-        for (int rep = 0; rep < REPS; ++rep) {
-            if (FULL || ok[rep]) {
-                T gv[NC], dw[NDIM];
-                blend_vjp<NDIM>(v[rep], tp[rep].w, g[rep], gv, dw);
+            for (int b = 0; b < BATCH; ++b) {
+                if (FULL || ok[b]) {
+                    gather<T, NDIM>(dp, tp[b], v[b]);
+                    g[b] = gp[b * ostride];
+                }
+            }
 #pragma unroll
-                for (int j = 0; j < NDIM; ++j) dg[rep][j] += dw[j];
-                if (DDATA) {
-                    T* q = ddn + (size_t)c * plane;
+            for (int b = 0; b < BATCH; ++b) {
+                if (FULL || ok[b]) {
+                    T gv[NC], dw[NDIM];
+                    blend_vjp<NDIM>(v[b], tp[b].w, g[b], gv, dw);
 #pragma unroll
-                    for (int u = 0; u < H; ++u) {
-                        atomicAdd(q + tp[rep].base[u], gv[u]);
-                        atomicAdd(q + tp[rep].base[u] + (tp[rep].two ? 1 : 0), gv[u + H]);
+                    for (int j = 0; j < NDIM; ++j) dg[r0 + b][j] += dw[j];
+                    if (DDATA) {
+#pragma unroll
+                        for (int u = 0; u < H; ++u) {
+                            atomicAdd(qd + tp[b].base[u], gv[u]);
+                            atomicAdd(qd + tp[b].base[u] + (tp[b].two ? 1 : 0), gv[u + H]);
+                        }
                     }
                 }
             }
+            if (DDATA) qd += plane;
         }
     }
     if (dgrid == nullptr) return;
@@ -460,19 +384,19 @@ __device__ __forceinline__ void interp_bwd_tile(const T* __restrict__ data, cons
     }
 }
 
-template <typename T, int NDIM>
-__global__ void __launch_bounds__(256)
+template <typename T, int NDIM, int BATCH, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_interp_bwd(const T* __restrict__ data, const T* __restrict__ grid, const T* __restrict__ gout,
              T* __restrict__ dgrid, T* __restrict__ ddata, Shape s)
 {
     __shared__ T sg[NDIM][TILE][TILE + 1];
     const bool full = (blockIdx.x * TILE + TILE <= s.O[0]) && (blockIdx.y * TILE + TILE <= s.O[NDIM - 1]);
     if (ddata != nullptr) {
-        if (full) interp_bwd_tile<T, NDIM, true, true>(data, grid, gout, dgrid, ddata, s, sg);
-        else interp_bwd_tile<T, NDIM, false, true>(data, grid, gout, dgrid, ddata, s, sg);
+        if (full) interp_bwd_tile<T, NDIM, true, true, BATCH>(data, grid, gout, dgrid, ddata, s, sg);
+        else interp_bwd_tile<T, NDIM, false, true, BATCH>(data, grid, gout, dgrid, ddata, s, sg);
     } else {
-        if (full) interp_bwd_tile<T, NDIM, true, false>(data, grid, gout, dgrid, ddata, s, sg);
-        else interp_bwd_tile<T, NDIM, false, false>(data, grid, gout, dgrid, ddata, s, sg);
+        if (full) interp_bwd_tile<T, NDIM, true, false, BATCH>(data, grid, gout, dgrid, ddata, s, sg);
+        else interp_bwd_tile<T, NDIM, false, false, BATCH>(data, grid, gout, dgrid, ddata, s, sg);
     }
 }
 
@@ -565,24 +489,25 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
     prof_begin(backward ? kProfInterpBwd : kProfInterpFwd, st);
     if (ndim == 2) {
         if (!backward) {
-            if (sizeof(T) == 4 && g_interp_variant >= 3) {
-                if constexpr (sizeof(T) == 4) {
-                    constexpr int STRIP = 4;
-                    dim3 gp((unsigned)(((s.O[0] + TILE - 1) / TILE + STRIP - 1) / STRIP), gy, (unsigned)z);
-                    if (g_interp_variant == 3) k_interp_fwd_pipe<T, 2, 2, STRIP, 4><<<gp, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
-                    else k_interp_fwd_pipe<T, 2, 4, STRIP, 3><<<gp, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
-                }
-            } else if (sizeof(T) == 4 && g_interp_variant == 1) k_interp_fwd<T, 2, 2, 6><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
-            else if (sizeof(T) == 4 && g_interp_variant == 2) k_interp_fwd<T, 2, 1, 8><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+            // (points in flight per thread, resident CTAs targeted); float32 only -- the check mode
+            // keeps the plain configuration
+            const int var = sizeof(T) == 4 ? g_interp_variant : 0;
+            if (var == 1) k_interp_fwd<T, 2, 1, 6><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+            else if (var == 2) k_interp_fwd<T, 2, 1, 8><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+            else if (var == 3) k_interp_fwd<T, 2, 2, 5><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+            else if (var == 4) k_interp_fwd<T, 2, 2, 4><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
             else k_interp_fwd<T, 2, 4, 1><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
         }
-        else k_interp_bwd<T, 2><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
+        else if (sizeof(T) == 4 && g_interp_variant == 0) k_interp_bwd<T, 2, 2, 3><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
+        else if (sizeof(T) == 4) k_interp_bwd<T, 2, 1, 5><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
+        else k_interp_bwd<T, 2, 1, 1><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
     } else {
         if (!backward) {
             if (sizeof(T) == 4 && g_interp_variant >= 1) k_interp_fwd<T, 3, 1, 4><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
             else k_interp_fwd<T, 3, 2, 1><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
         }
-        else k_interp_bwd<T, 3><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
+        else if (sizeof(T) == 4) k_interp_bwd<T, 3, 1, 3><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
+        else k_interp_bwd<T, 3, 1, 1><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (const T*)gout, (T*)out_or_dgrid, (T*)ddata, s);
     }
     prof_end(backward ? kProfInterpBwd : kProfInterpFwd, st);
     count_launch();
