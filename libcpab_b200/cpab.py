@@ -126,7 +126,8 @@ class Cpab(object):
     def transform_data(self, data, theta, outsize):
         self._check_type(data); self._check_device(data)
         self._check_type(theta); self._check_device(theta)
-        grid = self.uniform_meshgrid(outsize)
+        grid = self.backend.uniform_meshgrid(self.params.ndim, self.params.domain_min,
+                                             self.params.domain_max, outsize, self.device, _share=True)
         grid_t = self.transform_grid(grid, theta)
         return self.interpolate(data, grid_t, outsize)
 

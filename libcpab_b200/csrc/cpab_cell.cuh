@@ -47,6 +47,8 @@ struct Geom {
     float w[3];         // cell width rounded to float: `const float inc = 1.0 / n`
     float span[3];      // (float)(n * inc): the upper domain bound the reference compares with
     float khi[3];       // 2-D: column/row (already min'ed with n-1) of a coordinate clamped high
+    float spanm[3];     // 2-D: largest float below span (fast-path clamp)
+    float band2;        // 2-D: guard band of the diagonal tests
     float hi3[3];       // 3-D: clamp bound (float)(n*inc - 1e-8); z uses inc_x (cpab_ops.cpp:141)
     // ---- float64 check mode -------------------------------------------------------------------
     double wd[3];       // 1.0 / n
@@ -82,8 +84,12 @@ inline Geom make_geom(int ndim, const int* nc)
         const double top = (double)g.span[j] - 0.000000001;
         const double rem = fmod(top, (double)g.w[j]);
         g.khi[j] = (float)pick_min(n - 1, (top - rem) / (double)g.w[j]);
+        g.spanm[j] = nextafterf(g.span[j], 0.0f);
     }
     g.n_cells = (int)cells;
+    // |error| of the float local coordinates (3e-7) plus, for a coordinate clamped to spanm, the
+    // distance of its local coordinate from 1: (span - spanm)/w ~ n * 6e-8 (twice: it enters d1 and d2)
+    g.band2 = 2e-6f + 2.4e-7f * (float)(g.nc[0] > g.nc[1] ? g.nc[0] : g.nc[1]);
     for (int j = 0; j < 3; ++j) {
         const int wsel = (j == 2) ? 0 : j;                   // sic: nz * inc_x
         g.hi3[j] = (float)((double)((float)g.nc[j] * g.w[wsel]) - 1e-8);
@@ -197,32 +203,37 @@ CPAB_HD_NOINLINE int triangle_2d_exact(float rx, float ry, float wx, float wy)
     return x_lt_y ? (anti ? 2 : 3) : (anti ? 1 : 0);
 }
 
-// Fast path.  A coordinate at or below 0 is clamped to 0 (column 0, local coordinate 0), one at
-// or above the span takes the host-evaluated column and local coordinate 1; with those
-// substitutions the in-domain diagonal tests reproduce the reference's out-of-bound branches
-// (left -> 3, right -> 1, above -> 0, below -> 2) whenever a single axis is outside, and every
-// corner region (both axes outside) lands exactly on a diagonal, i.e. in the guard band, from
-// where the reference's own expression sequence is replayed.
+// Fast path.  Coordinates are clamped to [0, spanm] (spanm = the float just below the span): a
+// coordinate at or below 0 gets column 0 and local coordinate 0, one at or above the span gets
+// the last column and a local coordinate within n*6e-8 of 1.  With those values the in-domain
+// diagonal tests reproduce the reference's out-of-bound branches (left -> 3, right -> 1,
+// above -> 0, below -> 2) whenever a single axis is outside and the point is not within the
+// guard band of a diagonal; every corner region (both axes outside) lands on a diagonal, i.e. in
+// the band, from where the reference's own expression sequence is replayed.
 CPAB_HD int find_cell_2d(float p0, float p1, const Geom& g)
 {
     float kx, rx, ky, ry;
-    divmod_exact(fmaxf(p0, 0.0f), g.nf[0], g.w[0], kx, rx);
-    divmod_exact(fmaxf(p1, 0.0f), g.nf[1], g.w[1], ky, ry);
-    const bool hix = p0 >= g.span[0], hiy = p1 >= g.span[1];
-    kx = hix ? g.khi[0] : fminf(kx, g.nm1[0]);
-    ky = hiy ? g.khi[1] : fminf(ky, g.nm1[1]);
+    divmod_exact(fminf(fmaxf(p0, 0.0f), g.spanm[0]), g.nf[0], g.w[0], kx, rx);
+    divmod_exact(fminf(fmaxf(p1, 0.0f), g.spanm[1]), g.nf[1], g.w[1], ky, ry);
+    kx = fminf(kx, g.nm1[0]);
+    ky = fminf(ky, g.nm1[1]);
     // approximate local coordinates (|error| < 3e-7) and the two diagonal tests
-    const float xf = hix ? 1.0f : rx * g.nf[0];
-    const float yf = hiy ? 1.0f : ry * g.nf[1];
+    const float xf = rx * g.nf[0], yf = ry * g.nf[1];
     const float d1 = xf - yf;                               // < 0  <=>  x < y
     const float d2 = (1.0f - xf) - yf;                      // < 0  <=>  1 - x < y
     int tri;
-    if (fminf(fabsf(d1), fabsf(d2)) < 2e-6f) {              // rare: on/near a diagonal or a corner
-        if (!(p0 > 0.0f) | hix | !(p1 > 0.0f) | hiy) return find_cell_2d_replay<float>(p0, p1, g);
+    if (fminf(fabsf(d1), fabsf(d2)) < g.band2) {            // rare: on/near a diagonal or a corner
+        if (!(p0 > 0.0f) | (p0 >= g.span[0]) | !(p1 > 0.0f) | (p1 >= g.span[1]))
+            return find_cell_2d_replay<float>(p0, p1, g);
         tri = triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
     } else {
-        // (x<y, 1-x<y) -> (0,0):0 (0,1):1 (1,1):2 (1,0):3  ==  (x<y ? 3 : 0) ^ (1-x<y ? 1 : 0)
+        // (x<y, 1-x<y) -> (0,0):0 (0,1):1 (1,1):2 (1,0):3  ==  (x<y ? 3 : 0) ^ (1-x<y ? 1 : 0);
+        // outside the band d1, d2 are non-zero, so their sign bits are the comparisons
+#if defined(__CUDA_ARCH__)
+        tri = ((__float_as_int(d1) >> 31) & 3) ^ (int)((unsigned)__float_as_int(d2) >> 31);
+#else
         tri = (d1 < 0.0f ? 3 : 0) ^ (d2 < 0.0f ? 1 : 0);
+#endif
     }
     return 4 * (int)fmaf(ky, g.nf[0], kx) + tri;
 }

@@ -236,6 +236,17 @@ int theta_to_trels_t(const Geom& g, int nsteps, int n_theta, int d, const void* 
                      const void* theta, void* As, void* trels, cudaStream_t st)
 {
     constexpr int TT = NDIM == 1 ? 16 : (NDIM == 2 ? 8 : 4);
+    if (n_theta < 1024) {
+        // small batches: one (theta, cell) per thread keeps more SMs busy than reusing basis rows
+        dim3 grid1((unsigned)((g.n_cells + 127) / 128), (unsigned)n_theta);
+        prof_begin(kProfThetaToTrels, st);
+        k_theta_to_trels<T, NDIM, 1><<<grid1, 128, (size_t)d * sizeof(T), st>>>(
+            (const T*)basis_t, (const T*)theta, (T*)As, (T*)trels, g.n_cells, d, nsteps, n_theta);
+        prof_end(kProfThetaToTrels, st);
+        count_launch();
+        CPAB_CUDA_OK(cudaGetLastError());
+        return kOk;
+    }
     const long ty = (n_theta + TT - 1) / TT;
     if (ty > 65535) {
         // grid.y limit: process in slabs

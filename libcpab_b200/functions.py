@@ -100,17 +100,31 @@ def identity(d, n_sample=1, epsilon=0, device="cpu"):
     return torch.zeros(n_sample, d, dtype=torch.float32, device=_device(device)) + epsilon
 
 
-def uniform_meshgrid(ndim, domain_min, domain_max, n_points, device="cpu"):
+_MESHGRID_CACHE = {}
+
+
+def uniform_meshgrid(ndim, domain_min, domain_max, n_points, device="cpu", _share=False):
     """[ndim, nP] grid, first coordinate fastest (libcpab/pytorch/functions.py:102-108).
 
     The 1-D linspaces are evaluated on the host and uploaded (a few KB): torch's CPU and CUDA
     linspace kernels differ in the last bit, and a CPU-generated grid keeps the input
-    bit-identical to what the reference's CPU path integrates.
+    bit-identical to what the reference's CPU path integrates.  The result is cached per
+    (domain, size, device): the upload is a synchronous pageable copy that would otherwise stall
+    the launch queue at the start of every transform_data call.  A fresh copy is returned, so
+    callers may modify it.
     """
-    lin = [torch.linspace(domain_min[i], domain_max[i], n_points[i]).to(_device(device))
-           for i in range(ndim)]
-    mesh = torch.meshgrid(lin[::-1], indexing="ij")
-    return torch.cat([g.reshape(1, -1) for g in mesh[::-1]], dim=0)
+    dev = _device(device)
+    key = (ndim, tuple(float(v) for v in domain_min), tuple(float(v) for v in domain_max),
+           tuple(int(v) for v in n_points), str(dev))
+    grid = _MESHGRID_CACHE.get(key)
+    if grid is None:
+        lin = [torch.linspace(domain_min[i], domain_max[i], n_points[i]).to(dev) for i in range(ndim)]
+        mesh = torch.meshgrid(lin[::-1], indexing="ij")
+        grid = torch.cat([g.reshape(1, -1) for g in mesh[::-1]], dim=0).contiguous()
+        if len(_MESHGRID_CACHE) >= 16:
+            _MESHGRID_CACHE.pop(next(iter(_MESHGRID_CACHE)))
+        _MESHGRID_CACHE[key] = grid
+    return grid if _share else grid.clone()     # _share: internal read-only use (transform_data)
 
 
 def findcellidx(ndim, grid, nc):
