@@ -58,6 +58,13 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "cfg2_2d_t3x3_b64_256x256"
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# capture of this very command (profiles/r01_ncu_bench_cfg2_summary.txt); null for workloads
+# that were not captured
+NCU_TRAFFIC_BYTES = {
+    "cfg2_2d_t3x3_b64_256x256": {"k_backward": 34.24e6, "k_forward": 0.61e6, "k_interp_fwd": 51.54e6},
+}
+
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -84,7 +91,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -323,7 +330,9 @@ def run_gpu_arm(args):
         "peak_source": "FP32 FMA throughput measured in this run by cpab_b200_fp32_fma_probe "
                        "(MEASURED_PEAKS.json has no FP32 entry; nominal 74.4)",
         "algorithmic_flops_per_pair": F_BWD[ndim], "ms_per_launch": bwd_ms / max(bwd_n, 1) if bwd_n else None,
-        "share_of_step": kshare["backward"], "traffic": None,
+        "share_of_step": kshare["backward"],
+        "traffic": NCU_TRAFFIC_BYTES.get(args.workload, {}).get("k_backward"),
+        "algorithmic_bytes": pairs_rank * 4 * ndim + nP * 4 * ndim,   # grad_out + points (compute-bound kernel)
     }
     roofline["frac"] = roofline["achieved"] / roofline["peak"] if roofline["achieved"] else None
     i_ms, i_n = prof["interp_fwd"]
@@ -333,7 +342,8 @@ def run_gpu_arm(args):
         "achieved": interp_bytes / (i_ms / max(i_n, 1) * 1e-3) / 1e9 if i_n else None,
         "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s", "peak_source": peak_src,
         "algorithmic_bytes_per_point": 4 * ndim + 8 * C, "ms_per_launch": i_ms / max(i_n, 1) if i_n else None,
-        "share_of_step": kshare["interp_fwd"], "traffic": None,
+        "share_of_step": kshare["interp_fwd"],
+        "traffic": NCU_TRAFFIC_BYTES.get(args.workload, {}).get("k_interp_fwd"),
         "note": "the workload's images (16.8 MB) are L2-resident after the flush-free forward pass; "
                 "see profiles/ for the HBM-sized run",
     }

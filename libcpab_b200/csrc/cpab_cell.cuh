@@ -215,8 +215,8 @@ CPAB_HD int find_cell_2d(float p0, float p1, const Geom& g)
     float kx, rx, ky, ry;
     divmod_exact(fminf(fmaxf(p0, 0.0f), g.spanm[0]), g.nf[0], g.w[0], kx, rx);
     divmod_exact(fminf(fmaxf(p1, 0.0f), g.spanm[1]), g.nf[1], g.w[1], ky, ry);
-    kx = fminf(kx, g.nm1[0]);
-    ky = fminf(ky, g.nm1[1]);
+    // no clamp of kx, ky is needed: span = RN(n*w) and spanm is the float below it, so
+    // spanm < n*w exactly and floor(spanm / w) <= n - 1
     // approximate local coordinates (|error| < 3e-7) and the two diagonal tests
     const float xf = rx * g.nf[0], yf = ry * g.nf[1];
     const float d1 = xf - yf;                               // < 0  <=>  x < y
