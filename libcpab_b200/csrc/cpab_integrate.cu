@@ -354,12 +354,13 @@ __device__ __forceinline__ void flush_runs(T* __restrict__ Gg, int key, T* acc)
 }
 
 // resident CTAs per SM the register allocation is tuned for (float: 80 regs in 1-D/2-D, 128 in 3-D -- fewer registers spill)
-template <typename T, int NDIM, int BLOCK> struct BwdOcc {
-    static constexpr int kMinBlocks = sizeof(T) == 8 ? 1 : 65536 / (BLOCK * (NDIM == 3 ? 128 : 80));
+template <typename T, int NDIM, int SEG, int BLOCK> struct BwdOcc {
+    static constexpr int kRegs = NDIM == 3 ? (SEG <= 3 ? 102 : 128) : 80;
+    static constexpr int kMinBlocks = sizeof(T) == 8 ? 1 : 65536 / (BLOCK * kRegs);
 };
 
 template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BwdOcc<T, NDIM, BLOCK>::kMinBlocks))
+__global__ void __launch_bounds__(BLOCK, (BwdOcc<T, NDIM, SEG, BLOCK>::kMinBlocks))
 k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __restrict__ gout,
            T* __restrict__ G, T* __restrict__ dpoints, long nP, int broadcast, int nsteps,
            const __grid_constant__ Geom g, int chunks, int chunk_pts)
@@ -582,8 +583,9 @@ k_grad_epilogue(const T* __restrict__ G, const T* __restrict__ B, T* __restrict_
 static int g_tune_fwd_ppt = 1;        // points advanced concurrently per thread in k_forward
 static int g_tune_chunk_auto = 0;     // 1: choose the chunk so that the grid fills whole waves
 static int g_tune_chunk_pts = 2048;   // points of one theta handled by one CTA
-static int g_tune_bwd_seg = 5;        // checkpoint spacing of k_backward
+static int g_tune_bwd_seg = 0;        // 0 = auto (5 in 1-D/2-D, 3 in 3-D: fits 96 registers -> 5 CTAs/SM)       // checkpoint spacing of k_backward
 static int g_tune_bwd_block = 128;
+static int g_tune_bwd_stage = -1;     // 1: stage A[theta] in shared memory, 0: read it through L1, -1 = auto (0 in 3-D)
 
 int set_tuning(const char* key, int value)
 {
@@ -591,7 +593,8 @@ int set_tuning(const char* key, int value)
     if (k == "fwd_ppt" && (value == 1 || value == 2)) { g_tune_fwd_ppt = value; return kOk; }
     if (k == "chunk_pts" && value >= 256 && value % 256 == 0) { g_tune_chunk_pts = value; g_tune_chunk_auto = 0; return kOk; }
     if (k == "chunk_auto" && (value == 0 || value == 1)) { g_tune_chunk_auto = value; return kOk; }
-    if (k == "bwd_seg" && (value == 5 || value == 10)) { g_tune_bwd_seg = value; return kOk; }
+    if (k == "bwd_seg" && (value == 0 || value == 3 || value == 5 || value == 10)) { g_tune_bwd_seg = value; return kOk; }
+    if (k == "bwd_stage" && value >= -1 && value <= 1) { g_tune_bwd_stage = value; return kOk; }
     if (k == "bwd_block" && (value == 64 || value == 128 || value == 256)) { g_tune_bwd_block = value; return kOk; }
     if (k == "interp_variant" && value >= 0 && value <= 4) { set_interp_variant(value); return kOk; }
     set_error("unknown tuning key/value %s=%d", key, value);
@@ -772,10 +775,23 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
         rc = backward_launch<T, NDIM, SEG, SMEM, BLOCK>(g, nsteps, n_theta, nP, broadcast, points, \
                                                         As, gout, ws, dpoints, st, fits)
     // preferred configuration first, then progressively smaller shared-memory footprints
-    if (g_tune_bwd_seg == 5) {
-        if (g_tune_bwd_block == 256) TRY(5, true, 256);
-        if (g_tune_bwd_block == 64) TRY(5, true, 64);
-        TRY(5, true, 128);
+    // measured (profiles/): 3-D runs best with 3-step segments (96 registers, 5 CTAs/SM) and the
+    // per-theta matrices read through L1 instead of staged (shared memory then holds only the
+    // checkpoints and the cell trace); 1-D/2-D with 5-step segments and staged matrices
+    const int seg = g_tune_bwd_seg != 0 ? g_tune_bwd_seg : (NDIM == 3 ? 3 : 5);
+    const bool stage = g_tune_bwd_stage >= 0 ? g_tune_bwd_stage != 0 : NDIM != 3;
+    if (seg == 3) {
+        if (stage) { if (g_tune_bwd_block == 256) TRY(3, true, 256); TRY(3, true, 128); }
+        else { if (g_tune_bwd_block == 256) TRY(3, false, 256); TRY(3, false, 128); }
+    } else if (seg == 5) {
+        if (stage) {
+            if (g_tune_bwd_block == 256) TRY(5, true, 256);
+            if (g_tune_bwd_block == 64) TRY(5, true, 64);
+            TRY(5, true, 128);
+        } else {
+            if (g_tune_bwd_block == 256) TRY(5, false, 256);
+            TRY(5, false, 128);
+        }
     } else {
         if (g_tune_bwd_block == 256) TRY(10, true, 256);
         if (g_tune_bwd_block == 64) TRY(10, true, 64);

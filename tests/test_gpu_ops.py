@@ -260,13 +260,13 @@ def test_backward_other_step_counts_and_tuning():
     B32 = dev(g["B"], torch.float32)
     for nsteps in (1, 7, 23, 50, 101):
         ref = O.theta_grad(g["grid"], g["As"], bs_of(g["B"], nc), g["gout"], nc, nsteps, threads=8)
-        for seg, block in ((10, 128), (5, 64), (5, 256)):
+        for seg, block in ((10, 128), (5, 64), (5, 256), (3, 128)):
             try:
                 _lib.set_tuning("bwd_seg", seg)
                 _lib.set_tuning("bwd_block", block)
                 dth, _ = ops.backward_theta(dev(g["grid"]), dev(g["As"]), B32, dev(g["gout"]), nc, nsteps)
             finally:
-                _lib.set_tuning("bwd_seg", 5)
+                _lib.set_tuning("bwd_seg", 0)
                 _lib.set_tuning("bwd_block", 128)
             assert rel_err(dth.cpu().numpy(), ref) < F32_TOL, (nsteps, seg, block)
 

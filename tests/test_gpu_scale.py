@@ -80,7 +80,7 @@ def test_full_size_gradient_properties(tess, n_theta, size, kw):
         _lib.set_tuning("chunk_pts", 512)
         dv, _ = ops.backward_theta(grid, As, B, g1, tess, 50)
     finally:
-        _lib.set_tuning("bwd_seg", 5)
+        _lib.set_tuning("bwd_seg", 0)
         _lib.set_tuning("chunk_pts", 2048)
     assert rel_err(dv.cpu().numpy(), d1.cpu().numpy()) < 2e-5
     # oracle on a sub-sample of points, first theta

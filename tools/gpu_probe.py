@@ -95,10 +95,10 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
     _lib.set_tuning("chunk_auto", 1)
     bwd_line("chunk_auto")
     _lib.set_tuning("chunk_auto", 0)
-    for chunk in (1536, 2816, 4096):
-        _lib.set_tuning("chunk_pts", chunk)
-        bwd_line(f"chunk{chunk}")
-    _lib.set_tuning("chunk_pts", 2048)
+    for seg, stage, block in ((3, 1, 128), (3, 0, 128), (3, 0, 256), (5, 0, 128), (5, 0, 256)):
+        _lib.set_tuning("bwd_seg", seg); _lib.set_tuning("bwd_stage", stage); _lib.set_tuning("bwd_block", block)
+        bwd_line(f"seg{seg}_stage{stage}_block{block}")
+    _lib.set_tuning("bwd_seg", 0); _lib.set_tuning("bwd_stage", -1); _lib.set_tuning("bwd_block", 128)
     if variants:
         for seg in (5, 10):
             for block in (64, 128, 256):
@@ -107,7 +107,7 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
                     _lib.set_tuning("bwd_block", block)
                     _lib.set_tuning("chunk_pts", chunk)
                     bwd_line(f"seg{seg}_block{block}_chunk{chunk}")
-        _lib.set_tuning("bwd_seg", 5)
+        _lib.set_tuning("bwd_seg", 0)
         _lib.set_tuning("bwd_block", 128)
         _lib.set_tuning("chunk_pts", 2048)
 
