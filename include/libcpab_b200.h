@@ -140,6 +140,25 @@ int cpab_b200_backward_theta(int dtype, int flags, int ndim, const int* nc, int 
                              void* stream);
 
 /*
+ * Closed-form ("hit-time") integration, 1-D only; OPT-IN extension, no counterpart in the
+ * reference (which integrates with nstepsolver fixed steps in every backend, libcpab/cpab.py:77,
+ * libcpab/core/cpab_ops.cpp:240-253).  Implements the algorithm of Freifeld et al., TPAMI 2017:
+ * analytic flow to the cell boundary, hit time, cross, repeat to t = 1.  Takes the velocity
+ * matrices `As` (not Trels) and no step count.  ndim != 1 returns CPAB_ERR_UNSUPPORTED.
+ */
+int cpab_b200_forward_closed_form(int dtype, int ndim, const int* nc, int n_theta, long nP,
+                                  int broadcast, const void* points, const void* As, void* newpoints,
+                                  void* stream);
+
+/* Exact gradient of the above w.r.t. theta (and optionally the points); same workspace as
+ * cpab_b200_backward_theta. */
+int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int n_theta, int d,
+                                         long nP, int broadcast, const void* points, const void* As,
+                                         const void* basis, const void* grad_out, void* dtheta,
+                                         void* dpoints, void* workspace, size_t workspace_bytes,
+                                         void* stream);
+
+/*
  * Linear / bilinear / trilinear sampling.  Replaces interpolate(ndim, data, grid, outsize),
  * libcpab/pytorch/interpolation.py:12-172.
  *   data [N, C, in_size...]   grid [N, ndim, prod(out_size)]   out [N, C, out_size...]

@@ -14,7 +14,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SOURCES = ["cpab_abi.cu", "cpab_integrate.cu", "cpab_expm.cu", "cpab_interp.cu", "cpab_probe.cu"]
+SOURCES = ["cpab_abi.cu", "cpab_integrate.cu", "cpab_expm.cu", "cpab_interp.cu", "cpab_probe.cu", "cpab_closed1d.cu"]
 HEADERS = ["cpab_common.cuh", "cpab_cell.cuh", os.path.join("..", "..", "include", "libcpab_b200.h")]
 LIB = os.path.join(CSRC, "libcpab_b200.so")
 

@@ -37,6 +37,7 @@ class Cpab(object):
         p.use_slow = False
         p.fast_math = False        # extension: FMA-contracted forward (not bit-exact with the CPU ref)
         p.points_grad = False      # extension: return dL/dpoints (reference returns None)
+        p.closed_form = False      # extension (1-D): exact hit-time integration instead of nstepsolver steps
         p.nC = int({1: 1, 2: 4, 3: 5}[p.ndim] * np.prod(p.nc))
         p.params_pr_cell = p.ndim * (p.ndim + 1)
 

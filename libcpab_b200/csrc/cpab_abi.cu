@@ -218,6 +218,48 @@ int cpab_b200_backward_theta(int dtype, int flags, int ndim, const int* nc, int 
                            workspace_bytes, (cudaStream_t)stream);
 }
 
+int cpab_b200_forward_closed_form(int dtype, int ndim, const int* nc, int n_theta, long nP,
+                                  int broadcast, const void* points, const void* As, void* newpoints,
+                                  void* stream)
+{
+    if (!check_geom(dtype, ndim, nc)) return kErrArgument;
+    if (ndim != 1) {
+        set_error("closed-form integration exists in 1-D only (the hit time has no closed form in %d-D)", ndim);
+        return kErrUnsupported;
+    }
+    REQUIRE(n_theta >= 0 && nP >= 0, "negative size");
+    REQUIRE(broadcast == 0 || broadcast == 1, "broadcast must be 0 or 1");
+    REQUIRE(n_theta == 0 || nP == 0 || (points && As && newpoints), "NULL pointer argument");
+    return launch_closed1d_forward(dtype, make_geom(ndim, nc), n_theta, nP, broadcast, points, As,
+                                   newpoints, (cudaStream_t)stream);
+}
+
+int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int n_theta, int d,
+                                         long nP, int broadcast, const void* points, const void* As,
+                                         const void* basis, const void* grad_out, void* dtheta,
+                                         void* dpoints, void* workspace, size_t workspace_bytes,
+                                         void* stream)
+{
+    if (!check_geom(dtype, ndim, nc)) return kErrArgument;
+    if (ndim != 1) {
+        set_error("closed-form integration exists in 1-D only (the hit time has no closed form in %d-D)", ndim);
+        return kErrUnsupported;
+    }
+    REQUIRE(n_theta >= 0 && nP >= 0 && d >= 0, "negative size");
+    REQUIRE(broadcast == 0 || broadcast == 1, "broadcast must be 0 or 1");
+    REQUIRE(n_theta == 0 || d == 0 || (As && basis && dtheta && workspace), "NULL pointer argument");
+    REQUIRE(n_theta == 0 || nP == 0 || (points && grad_out), "NULL pointer argument");
+    const Geom g = make_geom(ndim, nc);
+    const size_t need = backward_workspace_bytes(dtype, g, n_theta);
+    if (workspace_bytes < need) { set_error("backward: workspace has %zu bytes, needs %zu", workspace_bytes, need); return kErrWorkspace; }
+    if (n_theta == 0 || d == 0) return kOk;
+    cudaStream_t st = (cudaStream_t)stream;
+    CPAB_CUDA_OK(cudaMemsetAsync(workspace, 0, need, st));
+    int rc = launch_closed1d_backward(dtype, g, n_theta, nP, broadcast, points, As, grad_out, workspace, dpoints, st);
+    if (rc != kOk) return rc;
+    return launch_grad_epilogue(dtype, workspace, basis, dtheta, n_theta, 2 * g.nc[0], d, st);
+}
+
 static int check_interp(int dtype, int ndim, int N, int C, const int* in_size, const int* out_size)
 {
     REQUIRE(dtype == kF32 || dtype == kF64, "bad dtype %d", dtype);

@@ -72,6 +72,14 @@ int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta
                     int broadcast, const void* points, const void* As, const void* basis,
                     const void* grad_out, void* dtheta, void* dpoints, void* workspace,
                     size_t workspace_bytes, cudaStream_t st);
+int launch_grad_epilogue(int dtype, const void* G, const void* basis, void* dtheta, int n_theta, int D,
+                         int d, cudaStream_t st);
+// cpab_closed1d.cu
+int launch_closed1d_forward(int dtype, const Geom& g, int n_theta, long nP, int broadcast,
+                            const void* points, const void* As, void* out, cudaStream_t st);
+int launch_closed1d_backward(int dtype, const Geom& g, int n_theta, long nP, int broadcast,
+                             const void* points, const void* As, const void* gout, void* G,
+                             void* dpoints, cudaStream_t st);
 // cpab_expm.cu
 int launch_theta_to_trels(int dtype, const Geom& g, int nsteps, int n_theta, int d,
                           const void* basis_t, const void* theta, void* As, void* trels,

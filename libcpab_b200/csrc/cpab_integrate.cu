@@ -822,6 +822,21 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
     return kOk;
 }
 
+int launch_grad_epilogue(int dtype, const void* G, const void* basis, void* dtheta, int n_theta, int D,
+                         int d, cudaStream_t st)
+{
+    if (n_theta == 0 || d == 0) return kOk;
+    constexpr int TT = 8;
+    dim3 grid((unsigned)((n_theta + TT - 1) / TT), (unsigned)((d + 127) / 128));
+    prof_begin(kProfEpilogue, st);
+    if (dtype == kF32) k_grad_epilogue<float, TT><<<grid, 128, 0, st>>>((const float*)G, (const float*)basis, (float*)dtheta, n_theta, D, d);
+    else k_grad_epilogue<double, TT><<<grid, 128, 0, st>>>((const double*)G, (const double*)basis, (double*)dtheta, n_theta, D, d);
+    prof_end(kProfEpilogue, st);
+    count_launch();
+    CPAB_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
 int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int d, long nP,
                     int broadcast, const void* points, const void* As, const void* basis,
                     const void* grad_out, void* dtheta, void* dpoints, void* workspace,

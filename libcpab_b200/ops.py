@@ -157,6 +157,40 @@ def backward_theta(points: torch.Tensor, As: torch.Tensor, basis: torch.Tensor,
     return dtheta, dpoints
 
 
+def forward_closed_form(points: torch.Tensor, As: torch.Tensor, nc) -> torch.Tensor:
+    """1-D closed-form (hit-time) integration; opt-in extension, not in the reference."""
+    points, As = _req(points, "points"), _req(As, "As")
+    n_theta = As.shape[0]
+    broadcast, ndim, nP = _points_layout(points, n_theta)
+    out = torch.empty((n_theta, ndim, nP), dtype=points.dtype, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.load().cpab_b200_forward_closed_form(_dtype_code(points), ndim, nc_array(nc), n_theta, nP,
+                                                        broadcast, points.data_ptr(), As.data_ptr(),
+                                                        out.data_ptr(), _stream()), "forward_closed_form")
+    return out
+
+
+def backward_theta_closed_form(points, As, basis, grad_out, nc, want_dpoints=False):
+    points, As = _req(points, "points"), _req(As, "As")
+    basis, grad_out = _req(basis, "basis"), _req(grad_out, "grad_out")
+    n_theta = As.shape[0]
+    D, d = basis.shape
+    broadcast, ndim, nP = _points_layout(points, n_theta)
+    lib = _lib.load()
+    code = _dtype_code(points)
+    ws_bytes = lib.cpab_b200_backward_workspace_bytes(code, ndim, nc_array(nc), n_theta)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=points.device)
+    dtheta = torch.empty((n_theta, d), dtype=points.dtype, device=points.device)
+    dpoints = torch.empty_like(grad_out) if want_dpoints else None
+    with torch.cuda.device(points.device):
+        check(lib.cpab_b200_backward_theta_closed_form(
+            code, ndim, nc_array(nc), n_theta, d, nP, broadcast, points.data_ptr(), As.data_ptr(),
+            basis.data_ptr(), grad_out.data_ptr(), dtheta.data_ptr(),
+            dpoints.data_ptr() if want_dpoints else None, ws.data_ptr(), ws_bytes, _stream()),
+            "backward_theta_closed_form")
+    return dtheta, dpoints
+
+
 def interpolate_forward(data: torch.Tensor, grid: torch.Tensor, outsize) -> torch.Tensor:
     """data [N,C,*in], grid [N,ndim,prod(outsize)] -> [N,C,*outsize]."""
     data, grid = _req(data, "data"), _req(grid, "grid")

@@ -50,8 +50,12 @@ class _CpabFunction(torch.autograd.Function):
     def forward(ctx, points, theta, params):
         B, Bt = _basis(params, theta.device, theta.dtype)
         As, trels = ops.theta_to_trels(theta, Bt, params.nc, params.nstepsolver)
-        newpoints = ops.forward(points, trels, params.nc, params.nstepsolver,
-                                fast_math=bool(getattr(params, "fast_math", False)))
+        ctx.closed_form = bool(getattr(params, "closed_form", False))
+        if ctx.closed_form:      # opt-in extension (1-D): exact hit-time integration, no step count
+            newpoints = ops.forward_closed_form(points, As, params.nc)
+        else:
+            newpoints = ops.forward(points, trels, params.nc, params.nstepsolver,
+                                    fast_math=bool(getattr(params, "fast_math", False)))
         ctx.save_for_backward(points, As, B)
         ctx.params = params
         ctx.points_need_grad = points.requires_grad and bool(getattr(params, "points_grad", False))
@@ -62,8 +66,12 @@ class _CpabFunction(torch.autograd.Function):
     def backward(ctx, grad):
         points, As, B = ctx.saved_tensors
         p = ctx.params
-        dtheta, dpoints = ops.backward_theta(points, As, B, grad.contiguous(), p.nc, p.nstepsolver,
-                                             want_dpoints=ctx.points_need_grad)
+        if ctx.closed_form:
+            dtheta, dpoints = ops.backward_theta_closed_form(points, As, B, grad.contiguous(), p.nc,
+                                                             want_dpoints=ctx.points_need_grad)
+        else:
+            dtheta, dpoints = ops.backward_theta(points, As, B, grad.contiguous(), p.nc, p.nstepsolver,
+                                                 want_dpoints=ctx.points_need_grad)
         if dpoints is not None and points.dim() == 2:
             dpoints = dpoints.sum(dim=0)          # one grid shared by every theta
         return dpoints, dtheta, None
@@ -78,4 +86,7 @@ def CPAB_transformer(points, theta, params):
         raise RuntimeError("libcpab_b200 runs on CUDA tensors only (backend='pytorch', device='gpu')")
     if points.dtype != theta.dtype:
         raise TypeError("grid and theta must have the same dtype")
+    if getattr(params, "closed_form", False) and params.ndim != 1:
+        raise NotImplementedError("closed_form integration exists in 1-D only: in 2-D/3-D the hit "
+                                  "time of a cell boundary has no closed form")
     return _CpabFunction.apply(points, theta, params)

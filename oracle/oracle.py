@@ -469,3 +469,51 @@ def interpolate_vjp(data: np.ndarray, grid: np.ndarray, outsize, gout: np.ndarra
             sign = 1.0 if bits[j] else -1.0
             dgrid[:, j] += sign * wj * gv * (sizes[j] - 1)
     return dgrid.astype(data.dtype), ddata.astype(data.dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# closed-form 1-D integration -- NOT part of the reference
+# --------------------------------------------------------------------------------------------
+
+def closed_form_1d(points: np.ndarray, As: np.ndarray, nc) -> np.ndarray:
+    """Exact flow of a 1-D CPA field for unit time (hit-time algorithm, Freifeld et al. 2017).
+
+    PARITY UNPINNED: the reference contains no closed-form integrator, so there is
+    nothing of the reference to restate or to take golden vectors from.  This float64 numpy
+    version is the checker of the opt-in `closed_form` mode; it is anchored to the reference's
+    semantics by convergence: the fixed-step scheme (`forward`) tends to it as nstepsolver grows
+    (tests/test_closed_form_oracle.py).
+
+    points [1,nP] or [n_theta,1,nP]; As [n_theta,nC,1,2] -> [n_theta,1,nP] (float64).
+    """
+    As = np.asarray(As, dtype=np.float64)
+    n_theta, n = As.shape[0], int(nc[0])
+    pts = np.asarray(points, dtype=np.float64)
+    x = np.broadcast_to(pts if pts.ndim == 3 else pts[None], (n_theta, 1, pts.shape[-1]))[:, 0].copy()
+    a_all, b_all = As[:, :, 0, 0], As[:, :, 0, 1]
+    rows = np.arange(n_theta)[:, None]
+    t = np.ones_like(x)
+    c = np.clip(np.floor(x * n), 0, n - 1).astype(np.int64)
+    for _ in range(n + 1):
+        a, b = a_all[rows, c], b_all[rows, c]
+        v = a * x + b
+        right = v > 0
+        cn = np.where(right, c + 1, c - 1)
+        ok = (v != 0) & (cn >= 0) & (cn < n)
+        xb = np.where(right, (c + 1) / n, c / n)
+        delta = xb - x
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z = np.where(ok, a * delta / np.where(v == 0, 1.0, v), 0.0)
+            L = np.where(np.abs(z) < 1e-8, 1.0 - z / 2, np.log1p(np.where(z > -1, z, 0.0)) / np.where(z == 0, 1.0, z))
+            th = np.where(ok & (z > -1), delta / np.where(v == 0, 1.0, v) * L, np.inf)
+        cross = th < t
+        if not cross.any():
+            break
+        x = np.where(cross, xb, x)
+        t = np.where(cross, t - th, t)
+        c = np.where(cross, np.clip(cn, 0, n - 1), c)
+    a, b = a_all[rows, c], b_all[rows, c]
+    z = a * t
+    with np.errstate(divide="ignore", invalid="ignore"):
+        phi = np.where(np.abs(z) < 1e-8, 1.0 + z / 2, np.expm1(z) / np.where(z == 0, 1.0, z))
+    return (x * np.exp(z) + b * t * phi)[:, None, :]
