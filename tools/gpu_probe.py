@@ -111,6 +111,12 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
         _lib.set_tuning("bwd_block", 128)
         _lib.set_tuning("chunk_pts", 2048)
 
+    if ndim == 1:   # opt-in closed-form mode (not in the reference)
+        med, best = timeit(lambda: ops.forward_closed_form(grid, As, tess))
+        emit(kind="forward_closed_form", cfg=name, ms=med, pairs_per_s=pairs / med * 1e3)
+        med, best = timeit(lambda: ops.backward_theta_closed_form(grid, As, B, gout, tess))
+        emit(kind="backward_closed_form", cfg=name, ms=med, pairs_per_s=pairs / med * 1e3)
+
     # interpolation on the transformed grid
     C = 1
     data = torch.rand((n_theta, C, *size), device="cuda")

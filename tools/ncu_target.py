@@ -30,6 +30,9 @@ gout = torch.randn(n_theta, len(tess), grid.shape[1], device="cuda")
 g2 = torch.randn_like(data)
 for _ in range(reps):
     As, Tr = ops.theta_to_trels(theta, Bt, tess, 50)
+    if which == "1d":
+        ops.forward_closed_form(grid, As, tess)
+        ops.backward_theta_closed_form(grid, As, B, gout, tess)
     gt = ops.forward(grid, Tr, tess, 50)
     out = ops.interpolate_forward(data, gt, size)
     ops.interpolate_backward(data, gt, g2, True, False)
