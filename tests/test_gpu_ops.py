@@ -325,3 +325,58 @@ def test_errors_are_raised_not_swallowed():
         ops.forward(dev(g["grid"]), dev(g["Trels"]), [3, 3], 0)                    # nstepsolver = 0
     with pytest.raises(_lib.CpabError):
         _lib.set_tuning("no_such_knob", 1)
+
+
+# ------------------------------------------------------------------- large tessellations / step counts
+def test_tessellation_too_large_for_shared_memory():
+    """[128,130] -> 66 560 simplices: matrices are read through L1 instead of staged, the cell
+    trace is 32-bit.  Random (not constraint-satisfying) fields: the kernels do not care."""
+    from libcpab_b200 import ops
+    rng = np.random.default_rng(5)
+    nc = [128, 130]
+    nC, d, n_theta, nP = 4 * 128 * 130, 3, 2, 3000
+    B = rng.normal(size=(nC * 6, d)).astype(np.float32) * 0.3
+    theta = rng.normal(size=(n_theta, d)).astype(np.float32)
+    As = O.theta_to_affine(B, theta, nc)
+    Tr = O.affine_to_trels(As)
+    pts = rng.uniform(-0.05, 1.05, (2, nP)).astype(np.float32)
+    got = ops.forward(dev(pts), dev(Tr), nc, 50).cpu().numpy()
+    assert np.array_equal(got, O.forward(pts, Tr, nc, 50))
+    gout = rng.normal(size=(n_theta, 2, nP)).astype(np.float32)
+    ref = O.theta_grad(pts, As, bs_of(B, nc), gout, nc, 50, threads=8)
+    dth, _ = ops.backward_theta(dev(pts), dev(As), dev(B), dev(gout), nc, 50)
+    assert rel_err(dth.cpu().numpy(), ref) < F32_TOL
+    As_g, Tr_g = ops.theta_to_trels(dev(theta), dev(np.ascontiguousarray(B.T)), nc, 50)
+    assert rel_err(As_g.cpu().numpy(), As) < 1e-6
+
+
+def test_many_solver_steps_and_the_limit():
+    from libcpab_b200 import _lib, ops
+    g = load_golden("d2_t3x3")
+    nc = g["nc"].tolist()
+    pts = np.ascontiguousarray(g["grid"][:, ::5])
+    gout = np.ascontiguousarray(g["gout"][:, :, ::5])
+    B32 = dev(g["B"], torch.float32)
+    for nsteps in (400, 1000):
+        ref = O.theta_grad(pts, g["As"], bs_of(g["B"], nc), gout, nc, nsteps, threads=8)
+        dth, _ = ops.backward_theta(dev(pts), dev(g["As"]), B32, dev(gout), nc, nsteps)
+        assert rel_err(dth.cpu().numpy(), ref) < F32_TOL, nsteps
+    with pytest.raises(_lib.CpabError, match="checkpoint memory"):
+        ops.backward_theta(dev(pts), dev(g["As"]), B32, dev(gout), nc, 20000)
+    # the forward has no such limit
+    Tr = O.affine_to_trels(g["As"], 20000)
+    out = ops.forward(dev(pts), dev(Tr), nc, 20000).cpu().numpy()
+    assert np.array_equal(out, O.forward(pts, Tr, nc, 20000))
+
+
+def test_non_finite_inputs_do_not_crash():
+    from libcpab_b200 import ops
+    g = load_golden("d2_t3x3")
+    nc = g["nc"].tolist()
+    pts = g["grid"][:, :64].copy()
+    pts[0, 3], pts[1, 7], pts[0, 11], pts[1, 12] = np.nan, np.inf, -np.inf, 1e30
+    out = ops.forward(dev(pts), dev(g["Trels"]), nc, 50).cpu().numpy()
+    keep = np.isfinite(pts).all(axis=0) & (np.abs(pts) < 10).all(axis=0)
+    assert np.array_equal(out[:, :, keep], O.forward(pts, g["Trels"], nc, 50)[:, :, keep])
+    idx = ops.findcellidx(dev(pts), nc).cpu().numpy()
+    assert idx.min() >= 0 and idx.max() < 36
