@@ -175,6 +175,29 @@ int cpab_b200_interpolate_backward(int dtype, int ndim, int N, int C, const int*
                                    const int* out_size, const void* data, const void* grid,
                                    const void* grad_out, void* dgrid, void* ddata, void* stream);
 
+/*
+ * Fused Cpab.transform_data (libcpab/cpab.py:304-331: uniform_meshgrid -> transform_grid ->
+ * interpolate) for a meshgrid `points` [ndim, prod(out_size)] shared by all thetas: the forward
+ * kernel samples `data` at the end of every trajectory, the adjoint kernel forms dL/d(grid_t) from
+ * the image gradient in its prologue.  Results are identical to cpab_b200_forward followed by
+ * cpab_b200_interpolate_forward (same arithmetic); two launches and the d/dgrid round trip less.
+ *   data [n_theta, C, in_size...]   grid_t [n_theta, ndim, nP] out (kept for the backward)
+ *   out  [n_theta, C, out_size...]
+ */
+int cpab_b200_transform_data_forward(int dtype, int flags, int ndim, const int* nc, int nsteps,
+                                     int n_theta, int C, const int* in_size, const int* out_size,
+                                     const void* points, const void* trels, const void* data,
+                                     void* grid_t, void* out, void* stream);
+
+/* dL/dtheta of the above from grad_out [n_theta, C, out_size...]; workspace as for
+ * cpab_b200_backward_theta.  (dL/ddata, if wanted, is cpab_b200_interpolate_backward's.) */
+int cpab_b200_transform_data_backward(int dtype, int ndim, const int* nc, int nsteps, int n_theta,
+                                      int d, int C, const int* in_size, const int* out_size,
+                                      const void* points, const void* As, const void* basis,
+                                      const void* data, const void* grid_t, const void* grad_out,
+                                      void* dtheta, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

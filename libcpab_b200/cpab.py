@@ -7,6 +7,8 @@ helpers (cpab.py:349-476) are not part of the hot path and are not provided.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import functions as _backend
@@ -38,6 +40,12 @@ class Cpab(object):
         p.fast_math = False        # extension: FMA-contracted forward (not bit-exact with the CPU ref)
         p.points_grad = False      # extension: return dL/dpoints (reference returns None)
         p.closed_form = False      # extension (1-D): exact hit-time integration instead of nstepsolver steps
+        # transform_data as one forward + one backward kernel (identical results, 5 launches instead
+        # of 8): None = automatic (1-D, where the fused accesses stay unit-stride, and launch-bound
+        # sizes; measured break-even ~8M pairs in 2-D/3-D, profiles/r01_fused_vs_unfused.txt),
+        # True / False force it.  LIBCPAB_B200_FUSED=0/1 overrides the default.
+        env = os.environ.get("LIBCPAB_B200_FUSED")
+        p.fused_transform_data = None if env is None else env != "0"
         p.nC = int({1: 1, 2: 4, 3: 5}[p.ndim] * np.prod(p.nc))
         p.params_pr_cell = p.ndim * (p.ndim + 1)
 
@@ -129,6 +137,16 @@ class Cpab(object):
         self._check_type(theta); self._check_device(theta)
         grid = self.backend.uniform_meshgrid(self.params.ndim, self.params.domain_min,
                                              self.params.domain_max, outsize, self.device, _share=True)
+        if grid.dtype != theta.dtype:
+            grid = grid.to(theta.dtype)          # float64 check mode
+        p = self.params
+        fused = getattr(p, "fused_transform_data", None)
+        if fused is None:
+            fused = p.ndim == 1 or theta.shape[0] * grid.shape[1] <= (1 << 23)
+        if (fused and not p.closed_form and data.dim() == p.ndim + 2
+                and data.shape[0] == theta.shape[0] and data.dtype == theta.dtype == grid.dtype):
+            from .transformer import fused_transform_data
+            return fused_transform_data(data, theta, grid, p, outsize)
         grid_t = self.transform_grid(grid, theta)
         return self.interpolate(data, grid_t, outsize)
 

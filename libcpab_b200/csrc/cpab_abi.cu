@@ -284,6 +284,40 @@ int cpab_b200_interpolate_forward(int dtype, int ndim, int N, int C, const int* 
                                  (cudaStream_t)stream);
 }
 
+int cpab_b200_transform_data_forward(int dtype, int flags, int ndim, const int* nc, int nsteps,
+                                     int n_theta, int C, const int* in_size, const int* out_size,
+                                     const void* points, const void* trels, const void* data,
+                                     void* grid_t, void* out, void* stream)
+{
+    if (!check_geom(dtype, ndim, nc)) return kErrArgument;
+    const int rc = check_interp(dtype, ndim, n_theta, C, in_size, out_size);
+    if (rc != kOk) return rc;
+    REQUIRE(nsteps > 0, "nstepsolver = %d must be positive", nsteps);
+    REQUIRE(n_theta == 0 || C == 0 || (points && trels && data && grid_t && out), "NULL pointer argument");
+    if (C == 0) return kOk;
+    return launch_transform_data_forward(dtype, flags, make_geom(ndim, nc), nsteps, n_theta, C, in_size,
+                                         out_size, points, trels, data, grid_t, out, (cudaStream_t)stream);
+}
+
+int cpab_b200_transform_data_backward(int dtype, int ndim, const int* nc, int nsteps, int n_theta,
+                                      int d, int C, const int* in_size, const int* out_size,
+                                      const void* points, const void* As, const void* basis,
+                                      const void* data, const void* grid_t, const void* grad_out,
+                                      void* dtheta, void* workspace, size_t workspace_bytes,
+                                      void* stream)
+{
+    if (!check_geom(dtype, ndim, nc)) return kErrArgument;
+    const int rc = check_interp(dtype, ndim, n_theta, C, in_size, out_size);
+    if (rc != kOk) return rc;
+    REQUIRE(nsteps > 0, "nstepsolver = %d must be positive", nsteps);
+    REQUIRE(d >= 0, "negative size");
+    REQUIRE(n_theta == 0 || d == 0 || (points && As && basis && data && grid_t && grad_out && dtheta && workspace),
+            "NULL pointer argument");
+    return launch_transform_data_backward(dtype, make_geom(ndim, nc), nsteps, n_theta, d, C, in_size,
+                                          out_size, points, As, basis, data, grid_t, grad_out, dtheta,
+                                          workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int cpab_b200_interpolate_backward(int dtype, int ndim, int N, int C, const int* in_size,
                                    const int* out_size, const void* data, const void* grid,
                                    const void* grad_out, void* dgrid, void* ddata, void* stream)

@@ -72,6 +72,15 @@ int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta
                     int broadcast, const void* points, const void* As, const void* basis,
                     const void* grad_out, void* dtheta, void* dpoints, void* workspace,
                     size_t workspace_bytes, cudaStream_t st);
+int launch_transform_data_forward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int C,
+                                  const int* in_size, const int* out_size, const void* points,
+                                  const void* trels, const void* data, void* grid_t, void* img,
+                                  cudaStream_t st);
+int launch_transform_data_backward(int dtype, const Geom& g, int nsteps, int n_theta, int d, int C,
+                                   const int* in_size, const int* out_size, const void* points,
+                                   const void* As, const void* basis, const void* data,
+                                   const void* grid_t, const void* gimg, void* dtheta, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t st);
 int launch_grad_epilogue(int dtype, const void* G, const void* basis, void* dtheta, int n_theta, int D,
                          int d, cudaStream_t st);
 // cpab_closed1d.cu

@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "cpab_common.cuh"
+#include "cpab_sample.cuh"
 
 // -DCPAB_FAST_BUILD instantiates only the float32 2-D kernels (SASS experiments; never shipped).
 #ifdef CPAB_FAST_BUILD
@@ -173,6 +174,65 @@ __device__ __forceinline__ void stage_block(T* dst, const T* __restrict__ src, i
 }
 
 // =====================================================================================================
+// fused transform_data: sampling epilogue of the forward, sampling-VJP prologue of the adjoint.
+// The integration kernels are issue-bound with idle memory bandwidth, the stand-alone sampling
+// kernels are latency-bound; one gather per trajectory at either end of a 50-step loop costs ~2 %
+// and removes two launches and the d/dgrid round trip.  Same arithmetic as cpab_interp.cu
+// (shared helpers), hence identical results.
+// =====================================================================================================
+template <int NDIM>
+__device__ __forceinline__ int image_index(long p, const Shape& s)
+{
+    // grid point p = i0 + O0 (i1 + O1 i2)  ->  offset in a [O0,O1(,O2)] image, last index fastest
+    const int O0 = s.O[0];
+    if (NDIM == 1) return (int)p;
+    const int q = (int)(p / O0), i0 = (int)(p - (long)q * O0);
+    if (NDIM == 2) return i0 * s.O[1] + q;
+    const int i2 = q / s.O[1], i1 = q - i2 * s.O[1];
+    return (i0 * s.O[1] + i1) * s.O[2] + i2;
+}
+
+template <typename T, int NDIM>
+__device__ __forceinline__ void sample_store(const T* pt, int n, long p, const T* __restrict__ data,
+                                             T* __restrict__ img, const Shape& s)
+{
+    const Taps<T, NDIM> tp = make_taps<T, NDIM>(pt, s);
+    const int plane = s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
+    const int nPo = s.O[0] * (NDIM >= 2 ? s.O[1] : 1) * (NDIM >= 3 ? s.O[2] : 1);
+    const T* dp = data + (size_t)n * s.C * plane;
+    T* op = img + (size_t)n * s.C * nPo + image_index<NDIM>(p, s);
+#pragma unroll 1
+    for (int c = 0; c < s.C; ++c, dp += plane, op += nPo) {
+        T v[1 << NDIM];
+        gather<T, NDIM>(dp, tp, v);
+        *op = blend<NDIM>(v, tp.w);
+    }
+}
+
+template <typename T, int NDIM>
+__device__ __forceinline__ void sample_vjp(const T* pt, int n, long p, const T* __restrict__ data,
+                                           const T* __restrict__ gimg, const Shape& s, T* lam)
+{
+    const Taps<T, NDIM> tp = make_taps<T, NDIM>(pt, s);
+    const int plane = s.S[0] * (NDIM >= 2 ? s.S[1] : 1) * (NDIM >= 3 ? s.S[2] : 1);
+    const int nPo = s.O[0] * (NDIM >= 2 ? s.O[1] : 1) * (NDIM >= 3 ? s.O[2] : 1);
+    const T* dp = data + (size_t)n * s.C * plane;
+    const T* gp = gimg + (size_t)n * s.C * nPo + image_index<NDIM>(p, s);
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) lam[j] = 0;
+#pragma unroll 1
+    for (int c = 0; c < s.C; ++c, dp += plane, gp += nPo) {
+        T v[1 << NDIM], gv[1 << NDIM], dw[NDIM];
+        gather<T, NDIM>(dp, tp, v);
+        blend_vjp<NDIM>(v, tp.w, *gp, gv, dw);
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) lam[j] += dw[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) lam[j] *= (T)(s.S[j] - 1);
+}
+
+// =====================================================================================================
 // findcellidx
 // =====================================================================================================
 template <typename T, int NDIM>
@@ -190,10 +250,11 @@ __global__ void __launch_bounds__(256) k_findcellidx(const T* __restrict__ pts, 
 // =====================================================================================================
 // forward: nsteps x { c = cell(p) ; p = Trels[theta][c] [p;1] }
 // =====================================================================================================
-template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT>
+template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT, bool SAMPLE>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 4 : 1))
 k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restrict__ out, long nP,
-          int broadcast, int nsteps, const __grid_constant__ Geom g, int chunks, int chunk_pts)
+          int broadcast, int nsteps, const __grid_constant__ Geom g, int chunks, int chunk_pts,
+          const T* __restrict__ data, T* __restrict__ img, const __grid_constant__ Shape sh)
 {
     constexpr int PPC = Dim<NDIM>::kPpc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -239,6 +300,7 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
             if (i < end) {
 #pragma unroll
                 for (int j = 0; j < NDIM; ++j) dst[i + (long)j * nP] = p[u][j];
+                if (SAMPLE) sample_store<T, NDIM>(p[u], theta, i, data, img, sh);
             }
         }
     }
@@ -359,11 +421,14 @@ template <typename T, int NDIM, int SEG, int BLOCK> struct BwdOcc {
     static constexpr int kMinBlocks = sizeof(T) == 8 ? 1 : 65536 / (BLOCK * kRegs);
 };
 
-template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
+// SAMPLE: `gout` holds the transformed grid (output of the forward) and the upstream gradient is
+// that of the sampled image, `gimg`; lambda_N is formed in the prologue (fused transform_data).
+template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK, bool SAMPLE>
 __global__ void __launch_bounds__(BLOCK, (BwdOcc<T, NDIM, SEG, BLOCK>::kMinBlocks))
 k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __restrict__ gout,
            T* __restrict__ G, T* __restrict__ dpoints, long nP, int broadcast, int nsteps,
-           const __grid_constant__ Geom g, int chunks, int chunk_pts)
+           const __grid_constant__ Geom g, int chunks, int chunk_pts,
+           const T* __restrict__ data, const T* __restrict__ gimg, const __grid_constant__ Shape sh)
 {
     constexpr int PPC = Dim<NDIM>::kPpc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -406,6 +471,12 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
             T p[NDIM], lam[NDIM];
 #pragma unroll
             for (int j = 0; j < NDIM; ++j) { p[j] = src[i + (long)j * nP]; lam[j] = gsrc[i + (long)j * nP]; }
+            if (SAMPLE) {       // gsrc is the transformed grid: turn it into dL/d(grid_t)
+                T pt[NDIM];
+#pragma unroll
+                for (int j = 0; j < NDIM; ++j) pt[j] = lam[j];
+                sample_vjp<T, NDIM>(pt, theta, i, data, gimg, sh, lam);
+            }
 
             // ---- pass 1: the RK2 trajectory.  Records the cell of every step and a checkpoint
             //      of p at the start of every segment; the only pass that searches cells.
@@ -652,12 +723,20 @@ static void pick_chunks(long nP, int n_theta, int block, int ctas_per_sm, int st
     chunks = (int)((nP + chunk_pts - 1) / chunk_pts);
 }
 
-template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT>
+struct SampleArgs {       // fused transform_data: images to sample from / to, their geometry
+    const void* data = nullptr;
+    void* img = nullptr;          // forward: sampled output image
+    const void* gimg = nullptr;   // backward: upstream gradient of the sampled image
+    Shape sh{};
+};
+
+template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT, bool SAMPLE = false>
 static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int broadcast,
-                          const void* points, const void* trels, void* out, cudaStream_t st)
+                          const void* points, const void* trels, void* out, cudaStream_t st,
+                          const SampleArgs& sa = SampleArgs())
 {
     const size_t smem = SMEM ? (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T) : 0;
-    auto kern = k_forward<T, NDIM, STRICT, SMEM, PPT>;
+    auto kern = k_forward<T, NDIM, STRICT, SMEM, PPT, SAMPLE>;
     if (smem > 48 * 1024)
         CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int chunks, chunk_pts, per_sm = 0;
@@ -667,7 +746,8 @@ static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int b
     if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
     prof_begin(kProfForward, st);
     kern<<<(unsigned)blocks, 256, smem, st>>>((const T*)points, (const T*)trels, (T*)out, nP,
-                                              broadcast, nsteps, g, chunks, chunk_pts);
+                                              broadcast, nsteps, g, chunks, chunk_pts,
+                                              (const T*)sa.data, (T*)sa.img, sa.sh);
     prof_end(kProfForward, st);
     count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
@@ -676,11 +756,18 @@ static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int b
 
 template <typename T, int NDIM>
 static int forward_t(int flags, const Geom& g, int nsteps, int n_theta, long nP, int broadcast,
-                     const void* points, const void* trels, void* out, cudaStream_t st)
+                     const void* points, const void* trels, void* out, cudaStream_t st,
+                     const SampleArgs* sa = nullptr)
 {
     const bool smem = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T) <= 160 * 1024;
     const bool strict = !(flags & kFlagFastMath);
     const int ppt = g_tune_fwd_ppt;
+    if (sa != nullptr) {       // fused sampling epilogue
+#define SARGS g, nsteps, n_theta, nP, broadcast, points, trels, out, st, *sa
+        if (smem) return strict ? forward_launch<T, NDIM, true, true, 1, true>(SARGS) : forward_launch<T, NDIM, false, true, 1, true>(SARGS);
+        return strict ? forward_launch<T, NDIM, true, false, 1, true>(SARGS) : forward_launch<T, NDIM, false, false, 1, true>(SARGS);
+#undef SARGS
+    }
 #define ARGS g, nsteps, n_theta, nP, broadcast, points, trels, out, st
     if (smem) {
         if (strict) return ppt == 2 ? forward_launch<T, NDIM, true, true, 2>(ARGS) : forward_launch<T, NDIM, true, true, 1>(ARGS);
@@ -736,7 +823,7 @@ size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta)
 template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
 static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int broadcast,
                            const void* points, const void* As, const void* gout, void* G,
-                           void* dpoints, cudaStream_t st, bool& fits)
+                           void* dpoints, cudaStream_t st, bool& fits, const SampleArgs* sa)
 {
     const int nseg = (nsteps + SEG - 1) / SEG;
     const size_t tbytes = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
@@ -744,19 +831,25 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
                         (size_t)nsteps * BLOCK * (g.n_cells > 65535 ? 4 : 2);
     fits = smem <= kMaxSmemBytes;
     if (!fits) return kOk;
-    auto kern = k_backward<T, NDIM, SEG, SMEM, BLOCK>;
-    if (smem > 48 * 1024)
-        CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int chunks, chunk_pts, per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
-    pick_chunks(nP, n_theta, BLOCK, per_sm, 1024 + (int)(tbytes / 64), chunks, chunk_pts);
-    const long long blocks = (long long)n_theta * chunks;
-    if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
-    prof_begin(kProfBackward, st);
-    kern<<<(unsigned)blocks, BLOCK, smem, st>>>((const T*)points, (const T*)As, (const T*)gout, (T*)G,
-                                                (T*)dpoints, nP, broadcast, nsteps, g, chunks, chunk_pts);
-    prof_end(kProfBackward, st);
-    count_launch();
+    auto launch = [&](auto kern, const SampleArgs& a) -> int {
+        if (smem > 48 * 1024)
+            CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int chunks, chunk_pts, per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
+        pick_chunks(nP, n_theta, BLOCK, per_sm, 1024 + (int)(tbytes / 64), chunks, chunk_pts);
+        const long long blocks = (long long)n_theta * chunks;
+        if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+        prof_begin(kProfBackward, st);
+        kern<<<(unsigned)blocks, BLOCK, smem, st>>>((const T*)points, (const T*)As, (const T*)gout, (T*)G,
+                                                    (T*)dpoints, nP, broadcast, nsteps, g, chunks, chunk_pts,
+                                                    (const T*)a.data, (const T*)a.gimg, a.sh);
+        prof_end(kProfBackward, st);
+        count_launch();
+        return kOk;
+    };
+    const int rc = sa != nullptr ? launch(k_backward<T, NDIM, SEG, SMEM, BLOCK, true>, *sa)
+                                 : launch(k_backward<T, NDIM, SEG, SMEM, BLOCK, false>, SampleArgs());
+    if (rc != kOk) return rc;
     CPAB_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -764,7 +857,7 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
 template <typename T, int NDIM>
 static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, int broadcast,
                       const void* points, const void* As, const void* basis, const void* gout,
-                      void* dtheta, void* dpoints, void* ws, cudaStream_t st)
+                      void* dtheta, void* dpoints, void* ws, cudaStream_t st, const SampleArgs* sa = nullptr)
 {
     const int D = g.n_cells * Dim<NDIM>::kPpc;
     CPAB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)n_theta * D * sizeof(T), st));
@@ -773,7 +866,7 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
 #define TRY(SEG, SMEM, BLOCK)                                                                      \
     if (!fits && rc == kOk)                                                                        \
         rc = backward_launch<T, NDIM, SEG, SMEM, BLOCK>(g, nsteps, n_theta, nP, broadcast, points, \
-                                                        As, gout, ws, dpoints, st, fits)
+                                                        As, gout, ws, dpoints, st, fits, sa)
     // preferred configuration first, then progressively smaller shared-memory footprints
     // measured (profiles/): 3-D runs best with 3-step segments (96 registers, 5 CTAs/SM) and the
     // per-theta matrices read through L1 instead of staged (shared memory then holds only the
@@ -852,6 +945,65 @@ int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta
 #define GO(T) CPAB_DISPATCH((backward_t<T, 1>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)), \
                             (backward_t<T, 2>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)), \
                             (backward_t<T, 3>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)))
+    return CPAB_DTYPE(GO(float), GO(double));
+#undef GO
+}
+
+// ---- fused transform_data --------------------------------------------------------------------------
+static bool make_sample_shape(int ndim, int N, int C, const int* in_size, const int* out_size, Shape& sh, long& nP)
+{
+    sh.N = N; sh.C = C;
+    long long gridpts = 1, inpts = C;
+    for (int j = 0; j < 3; ++j) {
+        sh.S[j] = j < ndim ? in_size[j] : 1;
+        sh.O[j] = j < ndim ? out_size[j] : 1;
+        if (j < ndim) { gridpts *= out_size[j]; inpts *= in_size[j]; }
+    }
+    nP = (long)gridpts;
+    if (gridpts * ndim >= (1LL << 31) || inpts >= (1LL << 31) || gridpts * C >= (1LL << 31)) {
+        set_error("transform_data: one sample exceeds 2^31 elements");
+        return false;
+    }
+    return true;
+}
+
+int launch_transform_data_forward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int C,
+                                  const int* in_size, const int* out_size, const void* points,
+                                  const void* trels, const void* data, void* grid_t, void* img,
+                                  cudaStream_t st)
+{
+    SampleArgs sa;
+    long nP = 0;
+    if (!make_sample_shape(g.ndim, n_theta, C, in_size, out_size, sa.sh, nP)) return kErrUnsupported;
+    if (n_theta == 0 || nP == 0) return kOk;
+    sa.data = data;
+    sa.img = img;
+#define GO(T) CPAB_DISPATCH((forward_t<T, 1>(flags, g, nsteps, n_theta, nP, 0, points, trels, grid_t, st, &sa)), \
+                            (forward_t<T, 2>(flags, g, nsteps, n_theta, nP, 0, points, trels, grid_t, st, &sa)), \
+                            (forward_t<T, 3>(flags, g, nsteps, n_theta, nP, 0, points, trels, grid_t, st, &sa)))
+    return CPAB_DTYPE(GO(float), GO(double));
+#undef GO
+}
+
+int launch_transform_data_backward(int dtype, const Geom& g, int nsteps, int n_theta, int d, int C,
+                                   const int* in_size, const int* out_size, const void* points,
+                                   const void* As, const void* basis, const void* data,
+                                   const void* grid_t, const void* gimg, void* dtheta, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t st)
+{
+    SampleArgs sa;
+    long nP = 0;
+    if (!make_sample_shape(g.ndim, n_theta, C, in_size, out_size, sa.sh, nP)) return kErrUnsupported;
+    if (n_theta == 0 || d == 0) return kOk;
+    if (workspace_bytes < backward_workspace_bytes(dtype, g, n_theta)) {
+        set_error("backward: workspace has %zu bytes, needs %zu", workspace_bytes, backward_workspace_bytes(dtype, g, n_theta));
+        return kErrWorkspace;
+    }
+    sa.data = data;
+    sa.gimg = gimg;
+#define GO(T) CPAB_DISPATCH((backward_t<T, 1>(g, nsteps, n_theta, d, nP, 0, points, As, basis, grid_t, dtheta, nullptr, workspace, st, &sa)), \
+                            (backward_t<T, 2>(g, nsteps, n_theta, d, nP, 0, points, As, basis, grid_t, dtheta, nullptr, workspace, st, &sa)), \
+                            (backward_t<T, 3>(g, nsteps, n_theta, d, nP, 0, points, As, basis, grid_t, dtheta, nullptr, workspace, st, &sa)))
     return CPAB_DTYPE(GO(float), GO(double));
 #undef GO
 }

@@ -1,0 +1,146 @@
+// cpab_sample.cuh -- device helpers of the linear / bilinear / trilinear sampler, shared by the
+// stand-alone interpolate kernels (cpab_interp.cu) and the fused transform_data kernels
+// (cpab_integrate.cu).  Arithmetic follows libcpab/pytorch/interpolation.py:18-172 operation by
+// operation (every product and sum rounded separately), so that results are bit-identical to the
+// reference's float32 output for the same grid.
+#pragma once
+
+#include "cpab_common.cuh"
+
+namespace cpab {
+
+template <typename T> struct R;
+template <> struct R<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float flo(float a) { return floorf(a); }
+};
+template <> struct R<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double flo(double a) { return floor(a); }
+};
+
+struct Shape {
+    int N, C;
+    int S[3];   // input spatial sizes  (W, H, D)
+    int O[3];   // output spatial sizes (W_o, H_o, D_o)
+};
+
+// scale, floor, +1, clamp, weight (interpolation.py:29-47): returns clamped taps and xd
+template <typename T>
+__device__ __forceinline__ void taps(T gcoord, int size, int& t0, int& t1, T& wgt)
+{
+    const T hi = (T)(size - 1);
+    const T x = R<T>::mul(gcoord, hi);
+    const T f = R<T>::flo(x);
+    const T f0 = fmin(fmax(f, (T)0), hi);
+    const T f1 = fmin(fmax(f + (T)1, (T)0), hi);
+    t0 = (int)f0;
+    t1 = (int)f1;
+    wgt = R<T>::sub(x, f0);
+}
+
+// multilinear blend of 2^NDIM corner values, x first (bit 0), then y, then z
+template <int NDIM, typename T>
+__device__ __forceinline__ T blend(const T* v, const T* w)
+{
+    T a[1 << NDIM];
+#pragma unroll
+    for (int i = 0; i < (1 << NDIM); ++i) a[i] = v[i];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) {
+        const T om = R<T>::sub((T)1, w[j]);
+#pragma unroll
+        for (int m = 0; m < (1 << (NDIM - 1 - j)); ++m)
+            a[m] = R<T>::add(R<T>::mul(a[2 * m], om), R<T>::mul(a[2 * m + 1], w[j]));
+    }
+    return a[0];
+}
+
+// reverse of blend: corner weights gv[] (d out / d v) and dw[] (d out / d w_j), scaled by g
+template <int NDIM, typename T>
+__device__ __forceinline__ void blend_vjp(const T* v, const T* w, T g, T* gv, T* dw)
+{
+    // forward levels
+    T lev[NDIM + 1][1 << NDIM];
+#pragma unroll
+    for (int i = 0; i < (1 << NDIM); ++i) lev[0][i] = v[i];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j)
+#pragma unroll
+        for (int m = 0; m < (1 << (NDIM - 1 - j)); ++m)
+            lev[j + 1][m] = lev[j][2 * m] * ((T)1 - w[j]) + lev[j][2 * m + 1] * w[j];
+    T gl[1 << NDIM];
+    gl[0] = g;
+#pragma unroll
+    for (int j = NDIM - 1; j >= 0; --j) {
+        T acc = 0;
+#pragma unroll
+        for (int m = (1 << (NDIM - 1 - j)) - 1; m >= 0; --m) {
+            const T gm = gl[m];
+            acc += gm * (lev[j][2 * m + 1] - lev[j][2 * m]);
+            gl[2 * m + 1] = gm * w[j];
+            gl[2 * m] = gm * ((T)1 - w[j]);
+        }
+        dw[j] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < (1 << NDIM); ++i) gv[i] = gl[i];
+}
+
+constexpr int TILE = 32;
+constexpr int REPS = TILE / 8;
+
+// Per-point sampling state shared by forward and backward: for every corner of the leading
+// NDIM-1 dimensions the 32-bit element offset of the tap pair along the LAST (memory-fastest)
+// dimension, whether that pair really is two texels (it collapses to one at a clamped border),
+// and the interpolation weights.
+template <typename T, int NDIM> struct Taps {
+    int base[1 << (NDIM - 1)];   // offset of (x?,y?,.., last = t0)
+    bool two;                    // t1 != t0 along the last dimension
+    T w[NDIM];
+};
+
+template <typename T, int NDIM>
+__device__ __forceinline__ Taps<T, NDIM> make_taps(const T* gcoord, const Shape& s)
+{
+    Taps<T, NDIM> tp;
+    int t0[NDIM], t1[NDIM];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) taps(gcoord[j], s.S[j], t0[j], t1[j], tp.w[j]);
+    tp.two = t1[NDIM - 1] != t0[NDIM - 1];
+    if (NDIM == 1) {
+        tp.base[0] = t0[0];
+    } else if (NDIM == 2) {
+        tp.base[0] = t0[0] * s.S[1] + t0[1];
+        tp.base[1] = t1[0] * s.S[1] + t0[1];
+    } else {
+        const int r00 = t0[0] * s.S[1] + t0[1], r10 = t1[0] * s.S[1] + t0[1];
+        const int dy = t1[1] - t0[1];
+        tp.base[0] = r00 * s.S[2] + t0[2];
+        tp.base[1] = r10 * s.S[2] + t0[2];
+        tp.base[2] = (r00 + dy) * s.S[2] + t0[2];
+        tp.base[3] = (r10 + dy) * s.S[2] + t0[2];
+    }
+    return tp;
+}
+
+// gather the 2^NDIM corner values of one channel plane (corner bit j <-> dimension j)
+template <typename T, int NDIM>
+__device__ __forceinline__ void gather(const T* __restrict__ dp, const Taps<T, NDIM>& tp, T* v)
+{
+    constexpr int H = 1 << (NDIM - 1);
+#pragma unroll
+    for (int u = 0; u < H; ++u) {
+        const T* q = dp + tp.base[u];
+        const T lo = __ldg(q);
+        v[u] = lo;
+        v[u + H] = tp.two ? __ldg(q + 1) : lo;
+    }
+}
+
+
+}  // namespace cpab

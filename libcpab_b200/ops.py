@@ -233,3 +233,52 @@ def interpolate_backward(data: torch.Tensor, grid: torch.Tensor, grad_out: torch
 
 def ctypes_int_array(vals):
     return nc_array([int(v) for v in vals])
+
+
+def transform_data_forward(points: torch.Tensor, trels: torch.Tensor, data: torch.Tensor, nc,
+                           nsteps: int, outsize, fast_math: bool = False):
+    """Fused transform_data forward: integrate the shared meshgrid `points` [ndim,nP] for every
+    theta and sample `data` [n_theta,C,*in] at the end of each trajectory.  Returns
+    (out [n_theta,C,*outsize], grid_t [n_theta,ndim,nP]); identical to forward() + interpolate."""
+    points, trels, data = _req(points, "points"), _req(trels, "trels"), _req(data, "data")
+    ndim = len(nc)
+    n_theta, C = data.shape[:2]
+    outsize = [int(v) for v in outsize]
+    nP = int(np.prod(outsize))
+    if tuple(points.shape) != (ndim, nP):
+        raise ValueError(f"points has shape {tuple(points.shape)}, expected {(ndim, nP)}")
+    if trels.shape[0] != n_theta or data.dim() != ndim + 2:
+        raise ValueError("data, theta batch and tessellation dimension do not match")
+    if not (points.dtype == trels.dtype == data.dtype):
+        raise TypeError("points, trels and data must have the same dtype")
+    out = torch.empty((n_theta, C, *outsize), dtype=data.dtype, device=data.device)
+    grid_t = torch.empty((n_theta, ndim, nP), dtype=data.dtype, device=data.device)
+    flags = CPAB_FLAG_FAST_MATH if fast_math else 0
+    with torch.cuda.device(data.device):
+        check(_lib.load().cpab_b200_transform_data_forward(
+            _dtype_code(data), flags, ndim, nc_array(nc), int(nsteps), n_theta, C,
+            ctypes_int_array(data.shape[2:]), ctypes_int_array(outsize), points.data_ptr(),
+            trels.data_ptr(), data.data_ptr(), grid_t.data_ptr(), out.data_ptr(), _stream()),
+            "transform_data_forward")
+    return out, grid_t
+
+
+def transform_data_backward(points, As, basis, data, grid_t, grad_out, nc, nsteps: int):
+    """dL/dtheta of the fused transform_data from the image gradient grad_out [n_theta,C,*outsize]."""
+    points, As, basis = _req(points, "points"), _req(As, "As"), _req(basis, "basis")
+    data, grid_t, grad_out = _req(data, "data"), _req(grid_t, "grid_t"), _req(grad_out, "grad_out")
+    ndim = len(nc)
+    n_theta, C = data.shape[:2]
+    D, d = basis.shape
+    lib = _lib.load()
+    code = _dtype_code(data)
+    ws_bytes = lib.cpab_b200_backward_workspace_bytes(code, ndim, nc_array(nc), n_theta)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=data.device)
+    dtheta = torch.empty((n_theta, d), dtype=data.dtype, device=data.device)
+    with torch.cuda.device(data.device):
+        check(lib.cpab_b200_transform_data_backward(
+            code, ndim, nc_array(nc), int(nsteps), n_theta, d, C, ctypes_int_array(data.shape[2:]),
+            ctypes_int_array(grad_out.shape[2:]), points.data_ptr(), As.data_ptr(), basis.data_ptr(),
+            data.data_ptr(), grid_t.data_ptr(), grad_out.data_ptr(), dtheta.data_ptr(), ws.data_ptr(),
+            ws_bytes, _stream()), "transform_data_backward")
+    return dtheta

@@ -77,6 +77,43 @@ class _CpabFunction(torch.autograd.Function):
         return dpoints, dtheta, None
 
 
+class _TransformDataFunction(torch.autograd.Function):
+    """Cpab.transform_data as ONE forward and ONE backward kernel (plus the tiny theta->Trels and
+    G.B kernels): the sampler runs as the epilogue of the integration kernel and its VJP as the
+    prologue of the adjoint kernel.  Bit-identical to transform_grid followed by interpolate."""
+
+    @staticmethod
+    def forward(ctx, data, theta, grid, params, outsize):
+        B, Bt = _basis(params, theta.device, theta.dtype)
+        As, trels = ops.theta_to_trels(theta, Bt, params.nc, params.nstepsolver)
+        out, grid_t = ops.transform_data_forward(grid, trels, data, params.nc, params.nstepsolver, outsize,
+                                                 fast_math=bool(getattr(params, "fast_math", False)))
+        ctx.save_for_backward(data, grid, grid_t, As, B)
+        ctx.params = params
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        data, grid, grid_t, As, B = ctx.saved_tensors
+        p = ctx.params
+        grad = grad.contiguous()
+        dtheta = ddata = None
+        if ctx.needs_input_grad[1]:
+            dtheta = ops.transform_data_backward(grid, As, B, data, grid_t, grad, p.nc, p.nstepsolver)
+        if ctx.needs_input_grad[0]:
+            _, ddata = ops.interpolate_backward(data, grid_t, grad, want_dgrid=False, want_ddata=True)
+        return ddata, dtheta, None, None, None
+
+
+def fused_transform_data(data, theta, grid, params, outsize):
+    if not (data.is_cuda and theta.is_cuda and grid.is_cuda):
+        raise RuntimeError("libcpab_b200 runs on CUDA tensors only (backend='pytorch', device='gpu')")
+    if getattr(params, "use_slow", False) or getattr(params, "numeric_grad", False):
+        raise NotImplementedError("libcpab_b200 implements the fast analytic path only")
+    return _TransformDataFunction.apply(data, theta, grid, params, tuple(int(v) for v in outsize))
+
+
 def CPAB_transformer(points, theta, params):
     if getattr(params, "use_slow", False):
         raise NotImplementedError("libcpab_b200 has no slow (pure python) integrator")

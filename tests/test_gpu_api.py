@@ -173,3 +173,52 @@ def test_api_argument_checks_mirror_the_reference():
     assert idx.dtype == torch.int32 and int(idx.max()) < T.params.nC
     v = T.calc_vectorfield(grid, theta[:1])
     assert tuple(v.shape) == (2, 64)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if "data" in load_golden(n).files])
+def test_fused_transform_data_equals_the_unfused_composition(name):
+    """The fused kernels (sampling epilogue / VJP prologue) against transform_grid + interpolate
+    on the same inputs: forward bit-identical, gradients equal up to atomic summation order."""
+    g = load_golden(name)
+    T = make_T(g)
+    outsize = g["grid_n"].tolist()
+    res = {}
+    for fused in (True, False):
+        T.params.fused_transform_data = fused
+        theta = cuda(g["theta"]).requires_grad_(True)
+        data = cuda(g["data"]).requires_grad_(True)
+        out = T.transform_data(data, theta, outsize)
+        (out * cuda(g["data_gout"])).sum().backward()
+        res[fused] = (out.detach().cpu().numpy(), theta.grad.cpu().numpy(), data.grad.cpu().numpy())
+    assert np.array_equal(res[True][0], res[False][0])
+    assert rel_err(res[True][1], res[False][1]) < 2e-6
+    # (data gradient: float atomics in a different order; outside the domain two taps with
+    #  weights like 4.2 and -3.2 land on one texel, so the order shows at the 1e-6 level)
+    assert rel_err(res[True][2], res[False][2]) < 2e-5
+
+
+def test_fused_transform_data_multichannel_and_fp64():
+    from libcpab_b200 import Cpab
+    torch.manual_seed(5)
+    for tess, shape, outsize in (([3, 2], (3, 4, 19, 23), [31, 17]), ([2, 2, 2], (2, 2, 7, 6, 5), [9, 8, 10]),
+                                 ([6], (4, 3, 50), [77])):
+        T = Cpab(tess, backend="pytorch", device="gpu")
+        for dt in (torch.float32, torch.float64):
+            theta0 = T.sample_transformation(shape[0]).to(dt)
+            data = torch.rand(shape, device="cuda", dtype=dt)
+            R = torch.randn(shape[0], shape[1], *outsize, device="cuda", dtype=dt)
+            T.params.basis = T.params.basis          # same basis object: cache reused per dtype
+            grads = []
+            for fused in (True, False):
+                T.params.fused_transform_data = fused
+                th = theta0.clone().requires_grad_(True)
+                grid = T.uniform_meshgrid(outsize).to(dt)
+                if fused:
+                    from libcpab_b200.transformer import fused_transform_data
+                    out = fused_transform_data(data, th, grid, T.params, outsize)
+                else:
+                    out = T.interpolate(data, T.transform_grid(grid, th), outsize)
+                (out * R).sum().backward()
+                grads.append((out.detach(), th.grad))
+            assert torch.equal(grads[0][0], grads[1][0])
+            assert rel_err(grads[0][1].cpu().numpy(), grads[1][1].cpu().numpy()) < (2e-6 if dt == torch.float32 else 1e-12)

@@ -21,9 +21,9 @@ def test_gpu_arm_line():
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
         assert k in d, k
     assert d["steps"] == 3 and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
-    assert d["gpu_launches"] >= 3 * 7
+    assert d["gpu_launches"] >= 3 * 5      # theta->Trels, fused forward, fused adjoint, R->G, G.B
     r = d["roofline"]
     assert r["bound"] == "fp32" and 0 < r["frac"] < 1.2 and r["unit"] == "TFLOP/s" and 50 < r["peak"] < 90
-    assert 0 < d["roofline_interp"]["frac"] < 1.2 and d["roofline_interp"]["bound"] == "hbm"
+    assert d["roofline_interp"]["bound"] == "hbm" and 0 < d["roofline_interp"]["frac"] < 1.2
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 64 * 34 * 4 + 64 * 256 * 256 * 4 and e["d2h_bytes_per_step"] > 0
