@@ -121,7 +121,8 @@ int cpab_b200_backward_jacobian(int dtype, int ndim, const int* nc, int nsteps, 
                                 long nP, int broadcast, const void* points, const void* As,
                                 const void* Bs, void* jac, void* stream);
 
-/* Bytes of scratch cpab_b200_backward_theta needs (G, [n_theta, D]). */
+/* Bytes of scratch cpab_b200_backward_theta needs: the per-cell gradient G [n_theta, D] followed by
+ * the per-cell RK2 step records [n_theta, nC, 4|8|16].  The workspace must be 16-byte aligned. */
 size_t cpab_b200_backward_workspace_bytes(int dtype, int ndim, const int* nc, int n_theta);
 
 /*

@@ -66,9 +66,11 @@ def load() -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
-        if not os.path.exists(path):
-            _build.build()          # raises if nvcc is missing: no silent fallback
+        path = os.environ.get("LIBCPAB_B200_SO")      # development: an experimental build of the same ABI
+        if not path:
+            path = _build.LIB
+            if not os.path.exists(path):
+                _build.build()      # raises if nvcc is missing: no silent fallback
         lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError = ABI mismatch, surfaced loudly

@@ -254,7 +254,7 @@ int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int
     if (workspace_bytes < need) { set_error("backward: workspace has %zu bytes, needs %zu", workspace_bytes, need); return kErrWorkspace; }
     if (n_theta == 0 || d == 0) return kOk;
     cudaStream_t st = (cudaStream_t)stream;
-    CPAB_CUDA_OK(cudaMemsetAsync(workspace, 0, need, st));
+    CPAB_CUDA_OK(cudaMemsetAsync(workspace, 0, backward_g_bytes(dtype, g, n_theta), st));
     int rc = launch_closed1d_backward(dtype, g, n_theta, nP, broadcast, points, As, grad_out, workspace, dpoints, st);
     if (rc != kOk) return rc;
     return launch_grad_epilogue(dtype, workspace, basis, dtheta, n_theta, 2 * g.nc[0], d, st);

@@ -47,7 +47,9 @@ struct Geom {
     float w[3];         // cell width rounded to float: `const float inc = 1.0 / n`
     float span[3];      // (float)(n * inc): the upper domain bound the reference compares with
     float khi[3];       // 2-D: column/row (already min'ed with n-1) of a coordinate clamped high
-    float spanm[3];     // 2-D: largest float below span (fast-path clamp)
+    float spanm[3];     // 2-D: largest float below span
+    float nup[3];       // 2-D: smallest float >= 1/w (multiplier of the one-sided column estimate)
+    float hi2[3];       // 2-D: fast-path clamp (<= spanm, estimate there is exact)
     float band2;        // 2-D: guard band of the diagonal tests
     float hi3[3];       // 3-D: clamp bound (float)(n*inc - 1e-8); z uses inc_x (cpab_ops.cpp:141)
     // ---- float64 check mode -------------------------------------------------------------------
@@ -87,9 +89,29 @@ inline Geom make_geom(int ndim, const int* nc)
         g.spanm[j] = nextafterf(g.span[j], 0.0f);
     }
     g.n_cells = (int)cells;
-    // |error| of the float local coordinates (3e-7) plus, for a coordinate clamped to spanm, the
-    // distance of its local coordinate from 1: (span - spanm)/w ~ n * 6e-8 (twice: it enters d1 and d2)
-    g.band2 = 2e-6f + 2.4e-7f * (float)(g.nc[0] > g.nc[1] ? g.nc[0] : g.nc[1]);
+    // 2-D one-sided column estimate (divmod_up): multiplier nup >= 1/w, and the largest clamp value
+    // at which the estimate is still the exact column n-1 (so that points on or beyond the upper
+    // domain edge -- where zero-boundary flows park them -- stay on the fast path)
+    float edge = 0.0f;
+    for (int j = 0; j < 3; ++j) {
+        const double inv = 1.0 / (double)g.w[j];
+        float nup = (float)inv;
+        if ((double)nup < inv) nup = nextafterf(nup, 3.0e38f);
+        nup = nextafterf(nup, 3.0e38f);      // one ulp of slack: 1/w above is itself rounded
+        g.nup[j] = nup;
+        float hi = g.spanm[j];
+        for (int it = 0; it < 64; ++it) {
+            const double kest = floor((double)hi * (double)nup);
+            if (kest <= (double)(g.nc[j] - 1) && (double)hi - kest * (double)g.w[j] >= 0.0) break;
+            hi = nextafterf(hi, 0.0f);
+        }
+        g.hi2[j] = hi;
+        const float gap = (g.span[j] - hi) * g.nf[j];
+        if (j < 2 && gap > edge) edge = gap;
+    }
+    // |error| of the float local coordinates (3e-7) plus, for a coordinate clamped to hi2, the
+    // distance of its local coordinate from 1: (span - hi2)/w (twice: it enters d1 and d2)
+    g.band2 = 2e-6f + 2.4f * edge;
     for (int j = 0; j < 3; ++j) {
         const int wsel = (j == 2) ? 0 : j;                   // sic: nz * inc_x
         g.hi3[j] = (float)((double)((float)g.nc[j] * g.w[wsel]) - 1e-8);
@@ -203,39 +225,82 @@ CPAB_HD_NOINLINE int triangle_2d_exact(float rx, float ry, float wx, float wy)
     return x_lt_y ? (anti ? 2 : 3) : (anti ? 1 : 0);
 }
 
-// Fast path.  Coordinates are clamped to [0, spanm] (spanm = the float just below the span): a
+// One-sided variant used by the 2-D search: with a multiplier nup >= 1/w and the FFMA rounding
+// *down*, the estimate is floor(p * nup) >= floor(p / w) and exceeds it by at most one (only when
+// p/w lies within n 2^-22 below an integer).  r = fma(-k, w, p) is exact for both, and negative
+// exactly when the estimate is one too large -- a rare event that the caller folds into its
+// guard-band branch instead of paying a compare and two predicated adds per axis and step.
+// `magic` is 1.5 * 2^23; kernels pass it in a register they made opaque to ptxas (an FFMA takes
+// one non-register operand: with the constant as an immediate the multiplier would be re-loaded
+// from the constant bank every step).
+CPAB_HD void divmod_up(float p, float nup, float w, float magic, float& kf, float& r)
+{
+#if defined(__CUDA_ARCH__)
+    kf = __fmaf_rd(p, nup, magic) - magic;
+#else
+    (void)magic;
+    kf = (float)floor((double)p * (double)nup);             // p * nup is exact in double
+#endif
+    r = fmaf(-kf, w, p);
+}
+
+// Rare path of find_cell_2d: a column/row estimate one too large, a point on or near a diagonal,
+// or a point outside the domain near a corner.
+CPAB_HD_NOINLINE int find_cell_2d_rare(float p0, float p1, float kx, float rx, float ky, float ry, const Geom& g)
+{
+    if (rx < 0.0f) { kx -= 1.0f; rx += g.w[0]; }
+    if (ry < 0.0f) { ky -= 1.0f; ry += g.w[1]; }
+    const float xf = rx * g.nf[0], yf = ry * g.nf[1];
+    const float d1 = xf - yf, d2 = (1.0f - xf) - yf;
+    int tri;
+    if (fminf(fabsf(d1), fabsf(d2)) < g.band2) {
+        if (!(p0 > 0.0f) | (p0 >= g.span[0]) | !(p1 > 0.0f) | (p1 >= g.span[1]))
+            return find_cell_2d_replay<float>(p0, p1, g);
+        if ((p0 > g.hi2[0]) | (p1 > g.hi2[1]))             // inside, but clamped for the estimate
+            return find_cell_2d_replay<float>(p0, p1, g);
+        tri = triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
+    } else {
+        tri = (d1 < 0.0f ? 3 : 0) ^ (d2 < 0.0f ? 1 : 0);
+    }
+    return 4 * (int)fmaf(ky, g.nf[0], kx) + tri;
+}
+
+// Fast path.  Coordinates are clamped to [0, hi2] (hi2 = a float just below the span): a
 // coordinate at or below 0 gets column 0 and local coordinate 0, one at or above the span gets
-// the last column and a local coordinate within n*6e-8 of 1.  With those values the in-domain
+// the last column and a local coordinate within band2/2.4 of 1.  With those values the in-domain
 // diagonal tests reproduce the reference's out-of-bound branches (left -> 3, right -> 1,
 // above -> 0, below -> 2) whenever a single axis is outside and the point is not within the
 // guard band of a diagonal; every corner region (both axes outside) lands on a diagonal, i.e. in
 // the band, from where the reference's own expression sequence is replayed.
-CPAB_HD int find_cell_2d(float p0, float p1, const Geom& g)
+// Returns true when the point needs find_cell_2d_rare (then `cell` is not set); the estimates are
+// handed back so that the caller can continue there.
+CPAB_HD bool find_cell_2d_fast(float p0, float p1, const Geom& g, float magic, int& cell,
+                               float& kx, float& rx, float& ky, float& ry)
 {
-    float kx, rx, ky, ry;
-    divmod_exact(fminf(fmaxf(p0, 0.0f), g.spanm[0]), g.nf[0], g.w[0], kx, rx);
-    divmod_exact(fminf(fmaxf(p1, 0.0f), g.spanm[1]), g.nf[1], g.w[1], ky, ry);
-    // no clamp of kx, ky is needed: span = RN(n*w) and spanm is the float below it, so
-    // spanm < n*w exactly and floor(spanm / w) <= n - 1
+    divmod_up(fminf(fmaxf(p0, 0.0f), g.hi2[0]), g.nup[0], g.w[0], magic, kx, rx);
+    divmod_up(fminf(fmaxf(p1, 0.0f), g.hi2[1]), g.nup[1], g.w[1], magic, ky, ry);
     // approximate local coordinates (|error| < 3e-7) and the two diagonal tests
     const float xf = rx * g.nf[0], yf = ry * g.nf[1];
     const float d1 = xf - yf;                               // < 0  <=>  x < y
     const float d2 = (1.0f - xf) - yf;                      // < 0  <=>  1 - x < y
-    int tri;
-    if (fminf(fabsf(d1), fabsf(d2)) < g.band2) {            // rare: on/near a diagonal or a corner
-        if (!(p0 > 0.0f) | (p0 >= g.span[0]) | !(p1 > 0.0f) | (p1 >= g.span[1]))
-            return find_cell_2d_replay<float>(p0, p1, g);
-        tri = triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
-    } else {
-        // (x<y, 1-x<y) -> (0,0):0 (0,1):1 (1,1):2 (1,0):3  ==  (x<y ? 3 : 0) ^ (1-x<y ? 1 : 0);
-        // outside the band d1, d2 are non-zero, so their sign bits are the comparisons
+    // (x<y, 1-x<y) -> (0,0):0 (0,1):1 (1,1):2 (1,0):3  ==  (x<y ? 3 : 0) ^ (1-x<y ? 1 : 0);
+    // outside the band d1, d2 are non-zero, so their sign bits are the comparisons
 #if defined(__CUDA_ARCH__)
-        tri = ((__float_as_int(d1) >> 31) & 3) ^ (int)((unsigned)__float_as_int(d2) >> 31);
+    const int tri = ((__float_as_int(d1) >> 31) & 3) ^ (int)((unsigned)__float_as_int(d2) >> 31);
 #else
-        tri = (d1 < 0.0f ? 3 : 0) ^ (d2 < 0.0f ? 1 : 0);
+    const int tri = (d1 < 0.0f ? 3 : 0) ^ (d2 < 0.0f ? 1 : 0);
 #endif
-    }
-    return 4 * (int)fmaf(ky, g.nf[0], kx) + tri;
+    cell = 4 * (int)fmaf(ky, g.nf[0], kx) + tri;
+    return (fminf(fabsf(d1), fabsf(d2)) < g.band2) | (rx < 0.0f) | (ry < 0.0f);
+}
+
+CPAB_HD int find_cell_2d(float p0, float p1, const Geom& g, float magic = 12582912.0f)
+{
+    float kx, rx, ky, ry;
+    int cell;
+    if (find_cell_2d_fast(p0, p1, g, magic, cell, kx, rx, ky, ry))
+        return find_cell_2d_rare(p0, p1, kx, rx, ky, ry, g);
+    return cell;
 }
 
 CPAB_HD int find_cell_2d(double p0, double p1, const Geom& g)
@@ -331,6 +396,26 @@ CPAB_HD int find_cell(const T* p, const Geom& g)
     if (NDIM == 1) return find_cell_1d(p[0], g);
     if (NDIM == 2) return find_cell_2d(p[0], p[1], g);
     return find_cell_3d(p[0], p[1], p[2], g);
+}
+
+// Loop form for the integration kernels.  find_cell_try computes the cell on the fast path and
+// returns true if the point needs the complete search instead (find_cell); the kernels vote on
+// that flag and leave their inner loop warp-uniformly, so that the loop body contains no call
+// (a call site pins live values to callee-saved registers and makes ptxas rebuild loop invariants
+// after it every step).  Only the float32 2-D search has a separate rare path.
+template <int NDIM> CPAB_HD bool find_cell_try(const float* p, const Geom& g, float magic, int& cell)
+{
+    if (NDIM == 2) {
+        float kx, rx, ky, ry;
+        return find_cell_2d_fast(p[0], p[1], g, magic, cell, kx, rx, ky, ry);
+    }
+    cell = find_cell<NDIM, float>(p, g);
+    return false;
+}
+template <int NDIM> CPAB_HD bool find_cell_try(const double* p, const Geom& g, float, int& cell)
+{
+    cell = find_cell<NDIM, double>(p, g);
+    return false;
 }
 
 }  // namespace cpab

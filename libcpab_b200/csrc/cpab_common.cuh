@@ -67,7 +67,8 @@ int launch_forward(int dtype, int flags, const Geom& g, int nsteps, int n_theta,
 int launch_jacobian(int dtype, const Geom& g, int nsteps, int n_theta, int d, long nP,
                     int broadcast, const void* points, const void* As, const void* Bs, void* jac,
                     cudaStream_t st);
-size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta);
+size_t backward_g_bytes(int dtype, const Geom& g, int n_theta);           // G [n_theta, D]
+size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta);   // G + RK2 step table
 int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int d, long nP,
                     int broadcast, const void* points, const void* As, const void* basis,
                     const void* grad_out, void* dtheta, void* dpoints, void* workspace,

@@ -63,6 +63,30 @@ template <> struct Num<double> {
     static __device__ __forceinline__ double atomic_add(double* p, double v) { return atomicAdd(p, v); }
 };
 
+// Fire-and-forget reduction of one cell's COUNT accumulators into G.  float32 uses the vector forms
+// (REDG.E.ADD.F32x2 / F32x4, sm_90+): a 2-D cell is 3 instructions instead of 6, a 3-D cell 3 instead
+// of 12 -- this code runs divergently (lanes leave cells at different steps), so its length is paid
+// per occurrence by the whole warp.  Needs addr 8-byte (COUNT % 4 != 0) / 16-byte aligned, which the
+// [n_theta][nC][ndim][ndim+1] layout of G gives for a 16-byte aligned workspace.
+template <int COUNT> __device__ __forceinline__ void red_cell(float* addr, const float* v)
+{
+    if (COUNT % 4 == 0) {
+#pragma unroll
+        for (int e = 0; e < COUNT; e += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                         :: "l"(addr + e), "f"(v[e]), "f"(v[e + 1]), "f"(v[e + 2]), "f"(v[e + 3]) : "memory");
+    } else {
+#pragma unroll
+        for (int e = 0; e < COUNT; e += 2)
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr + e), "f"(v[e]), "f"(v[e + 1]) : "memory");
+    }
+}
+template <int COUNT> __device__ __forceinline__ void red_cell(double* addr, const double* v)
+{
+#pragma unroll
+    for (int e = 0; e < COUNT; ++e) atomicAdd(addr + e, v[e]);
+}
+
 // ---- per-cell matrix fetch (vectorised; the row-major [n][n+1] block is 8/16-byte aligned) --------
 template <int NDIM> __device__ __forceinline__ void load_affine(const float* M, float* a)
 {
@@ -101,22 +125,37 @@ __device__ __forceinline__ void lds_vec(uint32_t addr, double* a, int n4, int n2
         asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a[2 * i]), "=d"(a[2 * i + 1]) : "r"(addr + 16 * i));
 }
 
-template <typename T, int NDIM, bool SMEM> struct CellTable {
-    static constexpr int PPC = Dim<NDIM>::kPpc;
+// 16-byte global loads of COUNT consecutive elements (COUNT * sizeof(T) a multiple of 16, aligned)
+template <typename T, int COUNT> __device__ __forceinline__ void load_vec16(const T* M, T* a)
+{
+    constexpr int PER = 16 / sizeof(T);
+    const int4* v = reinterpret_cast<const int4*>(M);
+#pragma unroll
+    for (int i = 0; i < COUNT / PER; ++i) {
+        const int4 t = __ldg(v + i);
+        memcpy(a + PER * i, &t, 16);
+    }
+}
+
+// STRIDE = elements per cell: the affine block itself (ndim (ndim+1)) for A / Trels tables, the
+// padded RK2 step record (StepRec) for the backward sweep.
+template <typename T, int NDIM, bool SMEM, int STRIDE = Dim<NDIM>::kPpc> struct CellTable {
     const T* gptr;
     uint32_t saddr;
     __device__ __forceinline__ void load(int c, T* a) const
     {
         if (SMEM) {
-            const uint32_t addr = saddr + (uint32_t)c * (uint32_t)(PPC * sizeof(T));
-            if (sizeof(T) == 4 && NDIM == 3) {
-#pragma unroll
-                for (int i = 0; i < 1; ++i) lds_vec(addr, a, 3, 0);
+            const uint32_t addr = saddr + (uint32_t)c * (uint32_t)(STRIDE * sizeof(T));
+            if ((STRIDE * sizeof(T)) % 16 == 0) {
+                if (sizeof(T) == 4) lds_vec(addr, a, STRIDE / 4, 0);
+                else lds_vec(addr, a, 0, STRIDE / 2);
             } else {
-                lds_vec(addr, a, 0, PPC / 2);
+                lds_vec(addr, a, 0, STRIDE / 2);
             }
+        } else if (STRIDE == Dim<NDIM>::kPpc) {
+            load_affine<NDIM>(gptr + (size_t)c * STRIDE, a);
         } else {
-            load_affine<NDIM>(gptr + (size_t)c * PPC, a);
+            load_vec16<T, STRIDE>(gptr + (size_t)c * STRIDE, a);
         }
     }
 };
@@ -268,14 +307,16 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
         T* sT = reinterpret_cast<T*>(smem_raw);
         stage_block(sT, tab.gptr, tsize);
         __syncthreads();
-        tab.saddr = (uint32_t)__cvta_generic_to_shared(sT);
+        tab.saddr = (uint32_t)__cvta_generic_to_shared(sT) & 0xffffffu;   // CTA-local offset (no cluster launch: rank bits are 0)
     }
     const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
     T* dst = out + (size_t)theta * NDIM * nP;
     const long begin = (long)chunk * chunk_pts;
     const long end = begin + chunk_pts < nP ? begin + chunk_pts : nP;
 
-    for (long base = begin + threadIdx.x; base < end; base += (long)blockDim.x * PPT) {
+    const float magic = 12582912.0f;     // 1.5 * 2^23, rounding constant of the 2-D cell search
+    for (long b0 = begin; b0 < end; b0 += (long)blockDim.x * PPT) {      // warp-uniform trip count
+        const long base = b0 + threadIdx.x;
         T p[PPT][NDIM];
 #pragma unroll
         for (int u = 0; u < PPT; ++u) {
@@ -283,16 +324,39 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
 #pragma unroll
             for (int j = 0; j < NDIM; ++j) p[u][j] = i < end ? src[i + (long)j * nP] : (T)0.25;
         }
-        for (int s = 0; s < nsteps; ++s) {
+        auto advance = [&](int u, int c) {
+            T a[PPC], q[NDIM];
+            tab.load(c, a);
+            if (STRICT) affine_strict<NDIM>(a, p[u], q); else affine_fma<NDIM>(a, p[u], q);
 #pragma unroll
-            for (int u = 0; u < PPT; ++u) {
-                const int c = find_cell<NDIM>(p[u], g);
-                T a[PPC], q[NDIM];
-                tab.load(c, a);
-                if (STRICT) affine_strict<NDIM>(a, p[u], q); else affine_fma<NDIM>(a, p[u], q);
+            for (int j = 0; j < NDIM; ++j) p[u][j] = q[j];
+        };
+        // The inner loop runs fast-path steps until some lane of the warp needs the complete cell
+        // search (a point on a diagonal, a corner outside the domain...; ~1e-5 per point and
+        // step); that one step is then done for the whole warp below and the loop resumes.
+        constexpr bool kHasRarePath = NDIM == 2 && sizeof(T) == 4;   // see find_cell_try
+        int s = 0;
+        if (!kHasRarePath) {
+            for (; s < nsteps; ++s) {
 #pragma unroll
-                for (int j = 0; j < NDIM; ++j) p[u][j] = q[j];
+                for (int u = 0; u < PPT; ++u) advance(u, find_cell<NDIM>(p[u], g));
             }
+        }
+        while (kHasRarePath) {
+#pragma unroll 2
+            for (; s < nsteps; ++s) {
+                int c[PPT];
+                bool rare = false;
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) rare |= find_cell_try<NDIM>(p[u], g, magic, c[u]);
+                if (__any_sync(0xffffffffu, rare)) break;
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) advance(u, c[u]);
+            }
+            if (s >= nsteps) break;
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) advance(u, find_cell<NDIM>(p[u], g));
+            ++s;
         }
 #pragma unroll
         for (int u = 0; u < PPT; ++u) {
@@ -375,16 +439,45 @@ k_jacobian(const T* __restrict__ points, const T* __restrict__ As, const T* __re
 // The reverse sweep needs p_n.  Trajectories are checkpointed every SEG steps in shared memory
 // during a first forward pass and recomputed segment by segment into registers.
 // =====================================================================================================
+// One RK2 (midpoint) step inside a cell is itself an affine map of the point:
+//     p+ = p + h (L pMid + t),  pMid = p + (h/2)(L p + t)   =>   p+ = p + (D p + s),
+//     D = h L + (h^2/2) L^2,    s = h t + (h^2/2) L t,
+// and the sensitivity recursion's M = I + h L + (h^2/2) L^2 is I + D.  k_prepare_backward
+// evaluates one record per (theta, cell) (in double, rounded once); the sweeps then cost one affine
+// map per step instead of two, and lambda_n = lambda_{n+1} + D^T lambda_{n+1}.
+//   * The point is advanced by an *increment*, so each step rounds like the reference's own
+//     `p += vMid * h` (no systematic error from storing 1 + D_ii in float).
+//   * D p and s cancel (zero-boundary fields: |L p|, |t| >> |v|), which would amplify the
+//     rounding of the stored D and s; the record therefore holds the map about an origin o inside
+//     the cell:  inc = D (p - o) + s',  s' = s + D o  -- |p - o| is at most a cell, s' is the
+//     increment at o itself, nothing cancels.
+// Record layout (StepRec<NDIM>::kStride elements, 16-byte multiple):
+//     D [n][n] row-major | s' [n] | o [n] | padding
+// 1-D keeps the plain pair (D, s) about the global origin: the loop there is bound by the
+// shared-memory data pipe, a 16-byte record costs twice the wavefronts of an 8-byte one (measured
+// 18 % on 8192 x 1024), and |L p|, |t| stay within a small multiple of |v| for 1-D tessellations.
+template <int NDIM> struct StepRec {
+    static constexpr bool kLocal = NDIM > 1;
+    static constexpr int kStride = NDIM == 1 ? 2 : NDIM == 2 ? 8 : 16;
+    static constexpr int kS = NDIM * NDIM;          // offset of s'
+    static constexpr int kO = NDIM * NDIM + NDIM;   // offset of o
+};
+
 template <int NDIM, typename T>
-__device__ __forceinline__ void rk2_step(const T* A, T* p, T h, T hh)
+__device__ __forceinline__ void step_inc(const T* W, T* p)
 {
-    T v[NDIM], pm[NDIM], vm[NDIM];
-    affine_fma<NDIM>(A, p, v);
+    T q[NDIM], inc[NDIM];
 #pragma unroll
-    for (int j = 0; j < NDIM; ++j) pm[j] = Num<T>::fma(hh, v[j], p[j]);
-    affine_fma<NDIM>(A, pm, vm);
+    for (int j = 0; j < NDIM; ++j) q[j] = StepRec<NDIM>::kLocal ? p[j] - W[StepRec<NDIM>::kO + j] : p[j];
 #pragma unroll
-    for (int j = 0; j < NDIM; ++j) p[j] = Num<T>::fma(h, vm[j], p[j]);
+    for (int r = 0; r < NDIM; ++r) {
+        T acc = W[StepRec<NDIM>::kS + r];
+#pragma unroll
+        for (int c = NDIM - 1; c >= 0; --c) acc = Num<T>::fma(W[r * NDIM + c], q[c], acc);
+        inc[r] = acc;
+    }
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) p[j] += inc[j];
 }
 
 // Final flush of the per-thread accumulators: the lanes of a warp are neighbouring points, so they
@@ -409,15 +502,15 @@ __device__ __forceinline__ void flush_runs(T* __restrict__ Gg, int key, T* acc)
             if (lane - off >= start) acc[e] += t;
         }
     }
-    if (tail && key >= 0) {
-#pragma unroll
-        for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gg + (size_t)key * PPC + e, acc[e]);
-    }
+    if (tail && key >= 0) red_cell<PPC>(Gg + (size_t)key * PPC, acc);
 }
 
+#ifndef CPAB_BWD_REGS
+#define CPAB_BWD_REGS 80
+#endif
 // resident CTAs per SM the register allocation is tuned for (float: 80 regs in 1-D/2-D, 128 in 3-D -- fewer registers spill)
 template <typename T, int NDIM, int SEG, int BLOCK> struct BwdOcc {
-    static constexpr int kRegs = NDIM == 3 ? (SEG <= 3 ? 102 : 128) : 80;
+    static constexpr int kRegs = NDIM == 3 ? (SEG <= 3 ? 102 : 128) : CPAB_BWD_REGS;
     static constexpr int kMinBlocks = sizeof(T) == 8 ? 1 : 65536 / (BLOCK * kRegs);
 };
 
@@ -425,7 +518,7 @@ template <typename T, int NDIM, int SEG, int BLOCK> struct BwdOcc {
 // that of the sampled image, `gimg`; lambda_N is formed in the prologue (fused transform_data).
 template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK, bool SAMPLE>
 __global__ void __launch_bounds__(BLOCK, (BwdOcc<T, NDIM, SEG, BLOCK>::kMinBlocks))
-k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __restrict__ gout,
+k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __restrict__ gout,
            T* __restrict__ G, T* __restrict__ dpoints, long nP, int broadcast, int nsteps,
            const __grid_constant__ Geom g, int chunks, int chunk_pts,
            const T* __restrict__ data, const T* __restrict__ gimg, const __grid_constant__ Shape sh)
@@ -434,31 +527,35 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int theta = blockIdx.x / chunks;
     const int chunk = blockIdx.x - theta * chunks;
+    constexpr int WS = StepRec<NDIM>::kStride;
     const int tsize = g.n_cells * PPC;
+    const int wsize = g.n_cells * WS;
     const int nseg = (nsteps + SEG - 1) / SEG;
 
-    // shared layout: [A block] (if SMEM), checkpoints [nseg][NDIM][BLOCK], cell trace
+    // shared layout: [step records] (if SMEM), checkpoints [nseg][NDIM][BLOCK], cell trace
     // [nsteps][BLOCK] (16-bit; 32-bit only for tessellations of >= 65536 simplices, which never
     // fit the staged path)
-    T* sA = reinterpret_cast<T*>(smem_raw);
-    T* ck = sA + (SMEM ? tsize : 0);
+    T* sW = reinterpret_cast<T*>(smem_raw);
+    T* ck = sW + (SMEM ? wsize : 0);
     unsigned short* ct16 = reinterpret_cast<unsigned short*>(ck + (size_t)nseg * NDIM * BLOCK);
     int* ct32 = reinterpret_cast<int*>(ct16);
     const bool wide = !SMEM && g.n_cells > 65535;
-    CellTable<T, NDIM, SMEM> tab;
-    tab.gptr = As + (size_t)theta * tsize;
+    CellTable<T, NDIM, SMEM, WS> tab;
+    tab.gptr = Ws + (size_t)theta * wsize;
     tab.saddr = 0;
     if (SMEM) {
-        stage_block(sA, tab.gptr, tsize);
+        stage_block(sW, tab.gptr, wsize);
         __syncthreads();
-        tab.saddr = (uint32_t)__cvta_generic_to_shared(sA);
+        tab.saddr = (uint32_t)__cvta_generic_to_shared(sW) & 0xffffffu;   // CTA-local offset (no cluster launch: rank bits are 0)
     }
     T* Gg = G + (size_t)theta * tsize;
+    // keep the base in registers: the flush blocks run divergently, often, and would otherwise
+    // rebuild it from the kernel parameters (11 uniform-datapath instructions per occurrence)
+    asm volatile("" : "+l"(Gg));
     const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
     const T* gsrc = gout + (size_t)theta * NDIM * nP;
     const long begin = (long)chunk * chunk_pts;
     const long end = begin + chunk_pts < nP ? begin + chunk_pts : nP;
-    const T h = (T)(1.0 / nsteps), hh = (T)(0.5 / nsteps), h2 = (T)(0.5 / nsteps / nsteps);
 
     for (long base = begin; base < end; base += BLOCK) {      // warp-uniform trip count
         const long i = base + threadIdx.x;
@@ -493,9 +590,9 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
                         if (wide) ct32[n * BLOCK + threadIdx.x] = c;
                         else ct16[n * BLOCK + threadIdx.x] = (unsigned short)c;
                         if (FULL || n + 1 < nsteps) {
-                            T a[PPC];
-                            tab.load(c, a);
-                            rk2_step<NDIM>(a, p, h, hh);
+                            T w[WS];
+                            tab.load(c, w);
+                            step_inc<NDIM>(w, p);
                         }
                     }
                 }
@@ -508,6 +605,7 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
                 constexpr bool FULL = decltype(full_tag)::value;
                 const int len = FULL ? SEG : nsteps - sg * SEG;
                 T ps[SEG][NDIM];
+                T w[WS];
                 int cs[SEG];
 #pragma unroll
                 for (int j = 0; j < NDIM; ++j) p[j] = ck[(sg * NDIM + j) * BLOCK + threadIdx.x];
@@ -519,9 +617,8 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
 #pragma unroll
                         for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
                         if (s + 1 < SEG && (FULL || s + 1 < len)) {
-                            T a[PPC];
-                            tab.load(cs[s], a);
-                            rk2_step<NDIM>(a, p, h, hh);
+                            tab.load(cs[s], w);       // (the compiler keeps these for the sweep below)
+                            step_inc<NDIM>(w, p);
                         }
                     }
                 }
@@ -529,13 +626,9 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
                 for (int s = SEG - 1; s >= 0; --s) {
                     if (FULL || s < len) {
                         const int c = cs[s];
-                        T a[PPC];
-                        tab.load(c, a);
+                        tab.load(c, w);
                         if (c != cur) {                 // left a cell: hand its sum to R[theta]
-                            if (cur >= 0) {
-#pragma unroll
-                                for (int e = 0; e < PPC; ++e) Num<T>::atomic_add(Gg + (size_t)cur * PPC + e, acc[e]);
-                            }
+                            if (cur >= 0) red_cell<PPC>(Gg + (size_t)cur * PPC, acc);
 #pragma unroll
                             for (int e = 0; e < PPC; ++e) acc[e] = 0;
                             cur = c;
@@ -548,22 +641,17 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
                                 acc[r * (NDIM + 1) + cc] = Num<T>::fma(lam[r], ps[s][cc], acc[r * (NDIM + 1) + cc]);
                             acc[r * (NDIM + 1) + NDIM] += lam[r];
                         }
-                        // lambda_n = M^T lambda_{n+1} = lambda + L^T (h lambda + (h^2/2) L^T lambda)
-                        T u[NDIM];
-#pragma unroll
-                        for (int r = 0; r < NDIM; ++r) {
-                            T t = a[r] * lam[0];
-#pragma unroll
-                            for (int j = 1; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], lam[j], t);
-                            u[r] = Num<T>::fma(h2, t, h * lam[r]);
-                        }
+                        // lambda_n = M^T lambda_{n+1} = lambda_{n+1} + D^T lambda_{n+1}
+                        T nl[NDIM];
 #pragma unroll
                         for (int r = 0; r < NDIM; ++r) {
                             T t = lam[r];
 #pragma unroll
-                            for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(a[j * (NDIM + 1) + r], u[j], t);
-                            lam[r] = t;
+                            for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(w[j * NDIM + r], lam[j], t);
+                            nl[r] = t;
                         }
+#pragma unroll
+                        for (int r = 0; r < NDIM; ++r) lam[r] = nl[r];
                     }
                 }
             };
@@ -576,6 +664,52 @@ k_backward(const T* __restrict__ points, const T* __restrict__ As, const T* __re
             }
         }
         flush_runs<T, PPC>(Gg, cur, acc);
+    }
+}
+
+// Per (theta, cell): the RK2 step record (see step_inc) from A_c = [L | t], and a zeroed R_c block.
+// Evaluated in double and rounded once.  The origin is the centre of the cell's square / cube (any
+// float near the cell serves: s' is formed from the rounded value).
+template <typename T, int NDIM>
+__global__ void __launch_bounds__(256)
+k_prepare_backward(const T* __restrict__ As, T* __restrict__ Ws, T* __restrict__ R, long n_blocks, int nsteps,
+                   const __grid_constant__ Geom g)
+{
+    constexpr int PPC = Dim<NDIM>::kPpc;
+    constexpr int M = NDIM + 1;
+    constexpr int WS = StepRec<NDIM>::kStride;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    double A[PPC];
+#pragma unroll
+    for (int e = 0; e < PPC; ++e) { A[e] = (double)As[i * PPC + e]; R[i * PPC + e] = 0; }
+    int box = (int)(i % g.n_cells) / (NDIM == 1 ? 1 : NDIM == 2 ? 4 : 5);
+    T o[NDIM];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) {
+        const int k = box % g.nc[j];
+        box /= g.nc[j];
+        o[j] = StepRec<NDIM>::kLocal ? (T)((k + 0.5) / g.nc[j]) : (T)0;
+    }
+    const double h = 1.0 / nsteps, h2 = 0.5 / nsteps / nsteps;
+    T* W = Ws + i * WS;
+#pragma unroll
+    for (int r = 0; r < NDIM; ++r) {
+        double sp = 0;
+#pragma unroll
+        for (int cc = 0; cc < M; ++cc) {                       // (L Atilde)[r][cc] = sum_k L[r][k] A[k][cc]
+            double t = 0;
+#pragma unroll
+            for (int k = 0; k < NDIM; ++k) t = ::fma(A[r * M + k], A[k * M + cc], t);
+            const double v = ::fma(h2, t, h * A[r * M + cc]);
+            if (cc < NDIM) { W[r * NDIM + cc] = (T)v; sp = ::fma(v, (double)o[cc], sp); }
+            else W[StepRec<NDIM>::kS + r] = (T)(v + sp);
+        }
+        if (StepRec<NDIM>::kLocal) W[StepRec<NDIM>::kO + r] = o[r];
+    }
+    if (StepRec<NDIM>::kLocal) {
+#pragma unroll
+        for (int e = StepRec<NDIM>::kO + NDIM; e < WS; ++e) W[e] = 0;
     }
 }
 
@@ -652,8 +786,8 @@ k_grad_epilogue(const T* __restrict__ G, const T* __restrict__ B, T* __restrict_
 // host launchers
 // =====================================================================================================
 static int g_tune_fwd_ppt = 1;        // points advanced concurrently per thread in k_forward
-static int g_tune_chunk_auto = 0;     // 1: choose the chunk so that the grid fills whole waves
-static int g_tune_chunk_pts = 2048;   // points of one theta handled by one CTA
+static int g_tune_chunk_auto = 1;     // 1: cut chunks finer when the grid would not fill the chip
+static int g_tune_chunk_pts = 1024;   // points of one theta handled by one CTA
 static int g_tune_bwd_seg = 0;        // 0 = auto (5 in 1-D/2-D, 3 in 3-D: fits 96 registers -> 5 CTAs/SM)       // checkpoint spacing of k_backward
 static int g_tune_bwd_block = 128;
 static int g_tune_bwd_stage = -1;     // 1: stage A[theta] in shared memory, 0: read it through L1, -1 = auto (0 in 3-D)
@@ -701,23 +835,20 @@ static int sm_count()
     return sms;
 }
 
-// Points of one theta handled by one CTA.  The grid is n_theta x chunks CTAs of equal work; with
-// `slots` CTAs resident on the chip the kernel takes ceil(grid/slots) waves, so among the
-// candidate chunk sizes pick the one minimising waves x (chunk + per-CTA staging overhead).
-// For large problems every candidate is within a percent and the default wins.
-static void pick_chunks(long nP, int n_theta, int block, int ctas_per_sm, int stage_cost, int& chunks, int& chunk_pts)
+// Points of one theta handled by one CTA.  Measured on one B200 (profiles/r01b_chunk_sweep.txt):
+// 1024 is within 1 % of the best size on every BASELINE shape -- smaller chunks concentrate the
+// resident CTAs on few thetas (the G reductions of one theta then collide in L2: 2-D [3,3]
+// backward 0.71 ms at 1024, 0.86 at 512, 1.31 at 256), larger ones quantise small problems into
+// few waves (0.83 ms at 4096).  Problems that cannot fill the chip at 1024 are cut finer.
+static void pick_chunks(long nP, int n_theta, int block, int ctas_per_sm, int& chunks, int& chunk_pts)
 {
     const int unit = block > 256 ? block : 256;
     chunk_pts = g_tune_chunk_pts;
     if (g_tune_chunk_auto && ctas_per_sm > 0) {
         const long slots = (long)sm_count() * ctas_per_sm;
-        double best = 1e300;
-        for (int c = 1024; c <= 4096; c += unit) {
-            const long per_theta = (nP + c - 1) / c;
-            const long waves = ((long)n_theta * per_theta + slots - 1) / slots;
-            const double cost = (double)waves * (c + stage_cost) * (c == g_tune_chunk_pts ? 0.999 : 1.0);
-            if (cost < best) { best = cost; chunk_pts = c; }
-        }
+        while (chunk_pts / 2 >= unit && (chunk_pts / 2) % unit == 0 &&
+               (long)n_theta * ((nP + chunk_pts - 1) / chunk_pts) < slots / 2)
+            chunk_pts /= 2;
     }
     if (nP < chunk_pts) chunk_pts = (int)((nP + unit - 1) / unit * unit);
     chunks = (int)((nP + chunk_pts - 1) / chunk_pts);
@@ -741,7 +872,7 @@ static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int b
         CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int chunks, chunk_pts, per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
-    pick_chunks(nP, n_theta, 256, per_sm, 512 + (int)(smem / 64), chunks, chunk_pts);
+    pick_chunks(nP, n_theta, 256, per_sm, chunks, chunk_pts);
     const long long blocks = (long long)n_theta * chunks;
     if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
     prof_begin(kProfForward, st);
@@ -814,19 +945,26 @@ int launch_jacobian(int dtype, const Geom& g, int nsteps, int n_theta, int d, lo
 #undef GO
 }
 
-size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta)
+// G [n_theta, D] (accumulated as R, converted in place) followed by the RK2 step table W [n_theta, D]
+size_t backward_g_bytes(int dtype, const Geom& g, int n_theta)
 {
     const size_t elt = dtype == kF32 ? 4 : 8;
     return (size_t)n_theta * g.n_cells * g.ndim * (g.ndim + 1) * elt;
 }
+size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta)
+{
+    const size_t elt = dtype == kF32 ? 4 : 8;
+    const int stride = g.ndim == 1 ? StepRec<1>::kStride : g.ndim == 2 ? StepRec<2>::kStride : StepRec<3>::kStride;
+    return ((backward_g_bytes(dtype, g, n_theta) + 15) & ~(size_t)15) + (size_t)n_theta * g.n_cells * stride * elt;
+}
 
 template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK>
 static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int broadcast,
-                           const void* points, const void* As, const void* gout, void* G,
+                           const void* points, const void* Ws, const void* gout, void* G,
                            void* dpoints, cudaStream_t st, bool& fits, const SampleArgs* sa)
 {
     const int nseg = (nsteps + SEG - 1) / SEG;
-    const size_t tbytes = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
+    const size_t tbytes = (size_t)g.n_cells * StepRec<NDIM>::kStride * sizeof(T);
     const size_t smem = (SMEM ? tbytes : 0) + (size_t)nseg * NDIM * BLOCK * sizeof(T) +
                         (size_t)nsteps * BLOCK * (g.n_cells > 65535 ? 4 : 2);
     fits = smem <= kMaxSmemBytes;
@@ -836,11 +974,11 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
             CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int chunks, chunk_pts, per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
-        pick_chunks(nP, n_theta, BLOCK, per_sm, 1024 + (int)(tbytes / 64), chunks, chunk_pts);
+        pick_chunks(nP, n_theta, BLOCK, per_sm, chunks, chunk_pts);
         const long long blocks = (long long)n_theta * chunks;
         if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
         prof_begin(kProfBackward, st);
-        kern<<<(unsigned)blocks, BLOCK, smem, st>>>((const T*)points, (const T*)As, (const T*)gout, (T*)G,
+        kern<<<(unsigned)blocks, BLOCK, smem, st>>>((const T*)points, (const T*)Ws, (const T*)gout, (T*)G,
                                                     (T*)dpoints, nP, broadcast, nsteps, g, chunks, chunk_pts,
                                                     (const T*)a.data, (const T*)a.gimg, a.sh);
         prof_end(kProfBackward, st);
@@ -860,13 +998,18 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
                       void* dtheta, void* dpoints, void* ws, cudaStream_t st, const SampleArgs* sa = nullptr)
 {
     const int D = g.n_cells * Dim<NDIM>::kPpc;
-    CPAB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)n_theta * D * sizeof(T), st));
+    const long n_blocks = (long)n_theta * g.n_cells;
+    // second part of the workspace (16-byte aligned): RK2 step records
+    T* Ws = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + (((size_t)n_theta * D * sizeof(T) + 15) & ~(size_t)15));
+    k_prepare_backward<T, NDIM><<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>((const T*)As, Ws, (T*)ws, n_blocks, nsteps, g);
+    CPAB_CUDA_OK(cudaGetLastError());
+    count_launch();
     bool fits = nP == 0;      // nothing to integrate: G stays zero, the epilogue writes dtheta = 0
     int rc = kOk;
 #define TRY(SEG, SMEM, BLOCK)                                                                      \
     if (!fits && rc == kOk)                                                                        \
         rc = backward_launch<T, NDIM, SEG, SMEM, BLOCK>(g, nsteps, n_theta, nP, broadcast, points, \
-                                                        As, gout, ws, dpoints, st, fits, sa)
+                                                        Ws, gout, ws, dpoints, st, fits, sa)
     // preferred configuration first, then progressively smaller shared-memory footprints
     // measured (profiles/): 3-D runs best with 3-step segments (96 registers, 5 CTAs/SM) and the
     // per-theta matrices read through L1 instead of staged (shared memory then holds only the
@@ -900,7 +1043,6 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
         return kErrUnsupported;
     }
     {
-        const long n_blocks = (long)n_theta * g.n_cells;
         k_r_to_g<T, NDIM><<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>((T*)ws, (const T*)As, n_blocks, nsteps);
         CPAB_CUDA_OK(cudaGetLastError());
         count_launch();
@@ -942,6 +1084,7 @@ int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta
                   backward_workspace_bytes(dtype, g, n_theta));
         return kErrWorkspace;
     }
+    if (reinterpret_cast<uintptr_t>(workspace) & 15) { set_error("backward: workspace must be 16-byte aligned"); return kErrArgument; }
 #define GO(T) CPAB_DISPATCH((backward_t<T, 1>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)), \
                             (backward_t<T, 2>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)), \
                             (backward_t<T, 3>(g, nsteps, n_theta, d, nP, broadcast, points, As, basis, grad_out, dtheta, dpoints, workspace, st)))
@@ -999,6 +1142,7 @@ int launch_transform_data_backward(int dtype, const Geom& g, int nsteps, int n_t
         set_error("backward: workspace has %zu bytes, needs %zu", workspace_bytes, backward_workspace_bytes(dtype, g, n_theta));
         return kErrWorkspace;
     }
+    if (reinterpret_cast<uintptr_t>(workspace) & 15) { set_error("backward: workspace must be 16-byte aligned"); return kErrArgument; }
     sa.data = data;
     sa.gimg = gimg;
 #define GO(T) CPAB_DISPATCH((backward_t<T, 1>(g, nsteps, n_theta, d, nP, 0, points, As, basis, grid_t, dtheta, nullptr, workspace, st, &sa)), \

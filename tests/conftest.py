@@ -64,3 +64,32 @@ def flow_gain(As):
     A = np.asarray(As, dtype=np.float64)
     n = A.shape[-2]
     return float(np.exp(np.abs(A[..., :n]).sum(-1).max()))
+
+
+def theta_errs(got, ref):
+    """Per-theta max|got-ref| / max|ref| (the global max: north_star's 'relative')."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    den = np.abs(ref).max() or 1.0
+    return np.abs(got - ref).reshape(len(ref), -1).max(axis=1) / den
+
+
+def assert_grad_parity(got, ref, tol=1e-5, flip_bound=2e-3):
+    """float32 theta-gradient against the reference's float32 gradient.
+
+    The discretised flow is piecewise affine in the point, so its Jacobian jumps across cell faces.
+    An RK2 iterate that lands within an ulp of a face is assigned to one or the other cell by any
+    implementation that does not reproduce every rounding of the reference's CPU build (its own
+    CUDA build, FMA-contracted by nvcc, does not either).  Such a "flip" happens about once per
+    1e6 (point, step) events and moves that theta's gradient by ~ h |A_c - A_c'| / nP ~ 1e-5..1e-4
+    relative -- the reference's float32 and float64 gradients differ by 5e-4 on BASELINE
+    configs[0] for the same reason (tests/test_oracle_pinned.py).  The float64 check mode, where
+    flips have probability ~1e-15, is held to 1e-10 with no exception.  Here: the bulk of the
+    thetas within `tol`, at most max(1, 10 %) flipped ones, and those within the flip bound.
+    """
+    errs = theta_errs(got, ref)
+    flipped = int((errs >= tol).sum())
+    assert flipped <= max(1, len(errs) // 10), (flipped, len(errs), np.sort(errs)[-5:])
+    if len(errs) >= 4:
+        assert np.median(errs) < tol, np.median(errs)
+    assert errs.max() < flip_bound, errs.max()

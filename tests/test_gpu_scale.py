@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_err
+from conftest import assert_grad_parity, rel_err
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -81,16 +81,24 @@ def test_full_size_gradient_properties(tess, n_theta, size, kw):
         dv, _ = ops.backward_theta(grid, As, B, g1, tess, 50)
     finally:
         _lib.set_tuning("bwd_seg", 0)
-        _lib.set_tuning("chunk_pts", 2048)
+        _lib.set_tuning("chunk_pts", 1024)
+        _lib.set_tuning("chunk_auto", 1)
     assert rel_err(dv.cpu().numpy(), d1.cpu().numpy()) < 2e-5
-    # oracle on a sub-sample of points, first theta
+    # oracle (the reference's float32 arithmetic) on a sub-sample of points, first thetas.
+    # The discretised flow is piecewise affine in p, so its Jacobian jumps across cell faces: a
+    # point whose float32 RK2 iterate lands within an ulp of a face can be assigned to the
+    # neighbouring cell by any implementation that does not reproduce the reference's roundings bit
+    # for bit (its own CUDA build, FMA-contracted by nvcc, included).  Such a flip happens about
+    # once per 1e6 (point, step) events and moves that theta's gradient by ~h |dA| / nP ~ 1e-4
+    # relative; everything else agrees to rounding (conftest.assert_grad_parity).
     rng = np.random.default_rng(5)
     sel = np.sort(rng.choice(nP, size=min(512, nP), replace=False))
     Bs = np.ascontiguousarray(B.cpu().numpy().T.reshape(B.shape[1], -1, len(tess), len(tess) + 1))
-    ref = O.theta_grad(grid[:, sel].cpu().numpy(), As[:1].cpu().numpy(), Bs,
-                       g1[:1][:, :, sel].cpu().numpy(), tess, 50, threads=8)
-    got, _ = ops.backward_theta(grid[:, sel].contiguous(), As[:1], B, g1[:1][:, :, sel].contiguous(), tess, 50)
-    assert rel_err(got.cpu().numpy(), ref) < 1e-5
+    n_chk = min(8, n_theta)
+    ref = O.theta_grad(grid[:, sel].cpu().numpy(), As[:n_chk].cpu().numpy(), Bs,
+                       g1[:n_chk][:, :, sel].cpu().numpy(), tess, 50, threads=8)
+    got, _ = ops.backward_theta(grid[:, sel].contiguous(), As[:n_chk], B, g1[:n_chk][:, :, sel].contiguous(), tess, 50)
+    assert_grad_parity(got.cpu().numpy(), ref, 1e-5)
 
 
 def test_theta_sharding_is_exact():

@@ -119,3 +119,22 @@ def test_sequential_fixture_is_reproduced():
         grid = O.forward(grid, O.affine_to_trels(As), [20], 50)
         assert rel_err(grid, g["grids"][i]) < 2e-4      # own float32 expm rounding, chained flows
     assert not np.any(g["dtheta0"]) and not np.any(g["dtheta1"]) and np.any(g["dtheta2"])
+
+
+def test_reference_gradient_moves_more_than_1e5_between_float32_and_float64():
+    """Evidence for conftest.assert_grad_parity: the reference's arithmetic (oracle, pinned above
+    bit for bit to the reference's float32 Jacobian) evaluated in float32 and in float64 on
+    BASELINE configs[0] gives theta-gradients that differ by far more than 1e-5 of the largest
+    entry, and the difference is concentrated in a few thetas -- cell assignments of near-face
+    iterates flip with the rounding, everything else agrees to rounding."""
+    from conftest import theta_errs
+    g = load_golden("cfg1_1d50")
+    nc = g["nc"].tolist()
+    g32 = O.theta_grad(g["grid"], g["As"], bs_of(g["B"], nc), g["gout"], nc, 50, threads=8)
+    assert rel_err(g32, g["dtheta"]) < 2e-7                      # oracle == reference (float32)
+    f8 = np.float64
+    g64 = O.theta_grad(g["grid"].astype(f8), g["As"].astype(f8), bs_of(g["B"], nc, f8), g["gout"].astype(f8),
+                       nc, 50, threads=8)
+    errs = theta_errs(g32, g64)
+    assert errs.max() > 2e-5, errs.max()
+    assert np.median(errs) < 5e-6, np.median(errs)

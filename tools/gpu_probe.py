@@ -82,7 +82,7 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
                 _lib.set_tuning("chunk_pts", chunk)
                 fwd_line(f"ppt{ppt}_chunk{chunk}")
         _lib.set_tuning("fwd_ppt", 1)
-        _lib.set_tuning("chunk_pts", 2048)
+        _lib.set_tuning("chunk_pts", 1024)
 
     gout = torch.randn(n_theta, ndim, nP, device="cuda")
 
@@ -109,7 +109,7 @@ def run_config(name, tess, n_theta, size, kw, peak, variants=True):
                     bwd_line(f"seg{seg}_block{block}_chunk{chunk}")
         _lib.set_tuning("bwd_seg", 0)
         _lib.set_tuning("bwd_block", 128)
-        _lib.set_tuning("chunk_pts", 2048)
+        _lib.set_tuning("chunk_pts", 1024)
 
     if ndim == 1:   # opt-in closed-form mode (not in the reference)
         med, best = timeit(lambda: ops.forward_closed_form(grid, As, tess))
