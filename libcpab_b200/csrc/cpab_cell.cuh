@@ -26,6 +26,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "cpab_f32x2.cuh"
+
 #if defined(__CUDACC__)
 #define CPAB_HD __host__ __device__ __forceinline__
 #define CPAB_HD_NOINLINE inline __host__ __device__ __noinline__
@@ -277,10 +279,24 @@ CPAB_HD_NOINLINE int find_cell_2d_rare(float p0, float p1, float kx, float rx, f
 CPAB_HD bool find_cell_2d_fast(float p0, float p1, const Geom& g, float magic, int& cell,
                                float& kx, float& rx, float& ky, float& ry)
 {
-    divmod_up(fminf(fmaxf(p0, 0.0f), g.hi2[0]), g.nup[0], g.w[0], magic, kx, rx);
-    divmod_up(fminf(fmaxf(p1, 0.0f), g.hi2[1]), g.nup[1], g.w[1], magic, ky, ry);
-    // approximate local coordinates (|error| < 3e-7) and the two diagonal tests
-    const float xf = rx * g.nf[0], yf = ry * g.nf[1];
+    const float c0 = fminf(fmaxf(p0, 0.0f), g.hi2[0]), c1 = fminf(fmaxf(p1, 0.0f), g.hi2[1]);
+    float xf, yf;
+#if defined(__CUDA_ARCH__)
+    // both axes at once (packed FP32, cpab_f32x2.cuh); per lane identical to divmod_up
+    const F2 pc = pk(c0, c1), mg = bc(magic);
+    const F2 kf = sub2(fma2_rm(pc, pk(g.nup[0], g.nup[1]), mg), mg);
+    const F2 r = fma2(kf, pk(-g.w[0], -g.w[1]), pc);
+    const F2 xy = mul2(r, pk(g.nf[0], g.nf[1]));
+    unpk(kf, kx, ky);
+    unpk(r, rx, ry);
+    unpk(xy, xf, yf);
+#else
+    divmod_up(c0, g.nup[0], g.w[0], magic, kx, rx);
+    divmod_up(c1, g.nup[1], g.w[1], magic, ky, ry);
+    xf = rx * g.nf[0];
+    yf = ry * g.nf[1];
+#endif
+    // xf, yf: approximate local coordinates (|error| < 3e-7); the two diagonal tests
     const float d1 = xf - yf;                               // < 0  <=>  x < y
     const float d2 = (1.0f - xf) - yf;                      // < 0  <=>  1 - x < y
     // (x<y, 1-x<y) -> (0,0):0 (0,1):1 (1,1):2 (1,0):3  ==  (x<y ? 3 : 0) ^ (1-x<y ? 1 : 0);

@@ -160,6 +160,14 @@ template <typename T, int NDIM, bool SMEM, int STRIDE = Dim<NDIM>::kPpc> struct 
     }
 };
 
+// Shared-memory record of one cell's Trels block in k_forward.  2-D float32: the 2x3 block is
+// re-ordered to [a00 a01 a10 a11 | a02 a12 . .] (32 bytes): one LDS.128 + one LDS.64 instead of
+// three LDS.64, and the four products of T [p;1] are two packed multiplies (a_r0, a_r1) * (p0, p1).
+template <typename T, int NDIM, bool SMEM> struct FwdRec {
+    static constexpr bool kPacked = SMEM && NDIM == 2 && sizeof(T) == 4;
+    static constexpr int kStride = kPacked ? 8 : Dim<NDIM>::kPpc;
+};
+
 // out = A [v;1] in the reference's left-to-right order with every product and sum rounded
 // (cpab_ops.cpp:192-206) -- bit-identical to the CPU reference.
 template <int NDIM, typename T>
@@ -296,16 +304,27 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
           const T* __restrict__ data, T* __restrict__ img, const __grid_constant__ Shape sh)
 {
     constexpr int PPC = Dim<NDIM>::kPpc;
+    constexpr bool kPacked = FwdRec<T, NDIM, SMEM>::kPacked;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int theta = blockIdx.x / chunks;
     const int chunk = blockIdx.x - theta * chunks;
     const int tsize = g.n_cells * PPC;
-    CellTable<T, NDIM, SMEM> tab;
+    CellTable<T, NDIM, SMEM, FwdRec<T, NDIM, SMEM>::kStride> tab;
     tab.gptr = trels + (size_t)theta * tsize;
     tab.saddr = 0;
     if (SMEM) {
         T* sT = reinterpret_cast<T*>(smem_raw);
-        stage_block(sT, tab.gptr, tsize);
+        if (kPacked) {
+            const float2* src2 = reinterpret_cast<const float2*>(tab.gptr);     // 24-byte blocks, 8-byte aligned
+            float4* dst4 = reinterpret_cast<float4*>(smem_raw);
+            for (int c = threadIdx.x; c < g.n_cells; c += blockDim.x) {
+                const float2 r0 = __ldg(src2 + 3 * c), r1 = __ldg(src2 + 3 * c + 1), r2 = __ldg(src2 + 3 * c + 2);
+                dst4[2 * c] = make_float4(r0.x, r0.y, r1.y, r2.x);               // a00 a01 a10 a11
+                dst4[2 * c + 1] = make_float4(r1.x, r2.y, 0.0f, 0.0f);            // a02 a12
+            }
+        } else {
+            stage_block(sT, tab.gptr, tsize);
+        }
         __syncthreads();
         tab.saddr = (uint32_t)__cvta_generic_to_shared(sT) & 0xffffffu;   // CTA-local offset (no cluster launch: rank bits are 0)
     }
@@ -325,11 +344,28 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
             for (int j = 0; j < NDIM; ++j) p[u][j] = i < end ? src[i + (long)j * nP] : (T)0.25;
         }
         auto advance = [&](int u, int c) {
-            T a[PPC], q[NDIM];
-            tab.load(c, a);
-            if (STRICT) affine_strict<NDIM>(a, p[u], q); else affine_fma<NDIM>(a, p[u], q);
+            if constexpr (kPacked) {
+                const uint32_t addr = tab.saddr + (uint32_t)c * 32u;
+                float a[4], t[2];
+                lds_vec(addr, a, 1, 0);
+                asm("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(t[0]), "=f"(t[1]) : "r"(addr + 16));
+                if (STRICT) {       // products packed, sums scalar and separately rounded (cpab_f32x2.cuh)
+                    const F2 P = pk(p[u][0], p[u][1]);
+                    const F2 m0 = mul2(pk(a[0], a[1]), P), m1 = mul2(pk(a[2], a[3]), P);
+                    p[u][0] = __fadd_rn(__fadd_rn(lo(m0), hi(m0)), t[0]);
+                    p[u][1] = __fadd_rn(__fadd_rn(lo(m1), hi(m1)), t[1]);
+                } else {
+                    const float x = p[u][0], y = p[u][1];
+                    p[u][0] = fmaf(a[0], x, fmaf(a[1], y, t[0]));
+                    p[u][1] = fmaf(a[2], x, fmaf(a[3], y, t[1]));
+                }
+            } else {
+                T a[PPC], q[NDIM];
+                tab.load(c, a);
+                if (STRICT) affine_strict<NDIM>(a, p[u], q); else affine_fma<NDIM>(a, p[u], q);
 #pragma unroll
-            for (int j = 0; j < NDIM; ++j) p[u][j] = q[j];
+                for (int j = 0; j < NDIM; ++j) p[u][j] = q[j];
+            }
         };
         // The inner loop runs fast-path steps until some lane of the warp needs the complete cell
         // search (a point on a diagonal, a corner outside the domain...; ~1e-5 per point and
@@ -452,7 +488,9 @@ k_jacobian(const T* __restrict__ points, const T* __restrict__ As, const T* __re
 //     the cell:  inc = D (p - o) + s',  s' = s + D o  -- |p - o| is at most a cell, s' is the
 //     increment at o itself, nothing cancels.
 // Record layout (StepRec<NDIM>::kStride elements, 16-byte multiple):
-//     D [n][n] row-major | s' [n] | o [n] | padding
+//     D [n][n] COLUMN-major | s' [n] | o [n] | padding
+// (column-major so that in 2-D a column, s' and o are register pairs straight out of two LDS.128:
+// the step is FADD2, FFMA2, FFMA2, FADD2 -- packed FP32, cpab_f32x2.cuh.)
 // 1-D keeps the plain pair (D, s) about the global origin: the loop there is bound by the
 // shared-memory data pipe, a 16-byte record costs twice the wavefronts of an 8-byte one (measured
 // 18 % on 8192 x 1024), and |L p|, |t| stay within a small multiple of |v| for 1-D tessellations.
@@ -461,23 +499,59 @@ template <int NDIM> struct StepRec {
     static constexpr int kStride = NDIM == 1 ? 2 : NDIM == 2 ? 8 : 16;
     static constexpr int kS = NDIM * NDIM;          // offset of s'
     static constexpr int kO = NDIM * NDIM + NDIM;   // offset of o
+    static __host__ __device__ constexpr int d(int r, int c) { return c * NDIM + r; }   // D[r][c]
 };
+
+template <int NDIM, typename T> struct UsePacked { static constexpr bool value = false; };
+template <> struct UsePacked<2, float> { static constexpr bool value = true; };
 
 template <int NDIM, typename T>
 __device__ __forceinline__ void step_inc(const T* W, T* p)
 {
-    T q[NDIM], inc[NDIM];
+    if constexpr (UsePacked<NDIM, T>::value) {
+        F2 P = pk(p[0], p[1]);
+        const F2 q = sub2(P, pk(W[6], W[7]));
+        F2 inc = fma2(pk(W[2], W[3]), bc(hi(q)), pk(W[4], W[5]));
+        inc = fma2(pk(W[0], W[1]), bc(lo(q)), inc);
+        P = add2(P, inc);
+        unpk(P, p[0], p[1]);
+    } else {
+        T q[NDIM], inc[NDIM];
 #pragma unroll
-    for (int j = 0; j < NDIM; ++j) q[j] = StepRec<NDIM>::kLocal ? p[j] - W[StepRec<NDIM>::kO + j] : p[j];
+        for (int j = 0; j < NDIM; ++j) q[j] = StepRec<NDIM>::kLocal ? p[j] - W[StepRec<NDIM>::kO + j] : p[j];
 #pragma unroll
-    for (int r = 0; r < NDIM; ++r) {
-        T acc = W[StepRec<NDIM>::kS + r];
+        for (int r = 0; r < NDIM; ++r) {
+            T acc = W[StepRec<NDIM>::kS + r];
 #pragma unroll
-        for (int c = NDIM - 1; c >= 0; --c) acc = Num<T>::fma(W[r * NDIM + c], q[c], acc);
-        inc[r] = acc;
+            for (int c = NDIM - 1; c >= 0; --c) acc = Num<T>::fma(W[StepRec<NDIM>::d(r, c)], q[c], acc);
+            inc[r] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) p[j] += inc[j];
     }
+}
+
+// R_c += lambda [p;1]^T.  The accumulators are held COLUMN-major, acc[c * n + r] = R[r][c] (so is
+// the R / G scratch until k_r_to_g): in 2-D a column is a register pair updated by one FFMA2.
+template <int NDIM, typename T>
+__device__ __forceinline__ void accumulate_outer(T* acc, const T* lam, const T* pn)
+{
+    if constexpr (UsePacked<NDIM, T>::value) {
+        const F2 L = pk(lam[0], lam[1]);
+        F2 a0 = fma2(L, bc(pn[0]), pk(acc[0], acc[1]));
+        F2 a1 = fma2(L, bc(pn[1]), pk(acc[2], acc[3]));
+        F2 a2 = add2(pk(acc[4], acc[5]), L);
+        unpk(a0, acc[0], acc[1]);
+        unpk(a1, acc[2], acc[3]);
+        unpk(a2, acc[4], acc[5]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < NDIM; ++j) p[j] += inc[j];
+        for (int r = 0; r < NDIM; ++r) {
+#pragma unroll
+            for (int cc = 0; cc < NDIM; ++cc) acc[cc * NDIM + r] = Num<T>::fma(lam[r], pn[cc], acc[cc * NDIM + r]);
+            acc[NDIM * NDIM + r] += lam[r];
+        }
+    }
 }
 
 // Final flush of the per-thread accumulators: the lanes of a warp are neighbouring points, so they
@@ -634,20 +708,14 @@ k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __re
                             cur = c;
                         }
                         // R_c += lambda_{n+1} [p_n;1]^T
-#pragma unroll
-                        for (int r = 0; r < NDIM; ++r) {
-#pragma unroll
-                            for (int cc = 0; cc < NDIM; ++cc)
-                                acc[r * (NDIM + 1) + cc] = Num<T>::fma(lam[r], ps[s][cc], acc[r * (NDIM + 1) + cc]);
-                            acc[r * (NDIM + 1) + NDIM] += lam[r];
-                        }
+                        accumulate_outer<NDIM>(acc, lam, ps[s]);
                         // lambda_n = M^T lambda_{n+1} = lambda_{n+1} + D^T lambda_{n+1}
                         T nl[NDIM];
 #pragma unroll
                         for (int r = 0; r < NDIM; ++r) {
                             T t = lam[r];
 #pragma unroll
-                            for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(w[j * NDIM + r], lam[j], t);
+                            for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(w[StepRec<NDIM>::d(j, r)], lam[j], t);
                             nl[r] = t;
                         }
 #pragma unroll
@@ -702,7 +770,7 @@ k_prepare_backward(const T* __restrict__ As, T* __restrict__ Ws, T* __restrict__
 #pragma unroll
             for (int k = 0; k < NDIM; ++k) t = ::fma(A[r * M + k], A[k * M + cc], t);
             const double v = ::fma(h2, t, h * A[r * M + cc]);
-            if (cc < NDIM) { W[r * NDIM + cc] = (T)v; sp = ::fma(v, (double)o[cc], sp); }
+            if (cc < NDIM) { W[StepRec<NDIM>::d(r, cc)] = (T)v; sp = ::fma(v, (double)o[cc], sp); }
             else W[StepRec<NDIM>::kS + r] = (T)(v + sp);
         }
         if (StepRec<NDIM>::kLocal) W[StepRec<NDIM>::kO + r] = o[r];
@@ -724,9 +792,14 @@ k_r_to_g(T* __restrict__ RG, const T* __restrict__ As, long n_blocks, int nsteps
     constexpr int M = NDIM + 1;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_blocks) return;
-    T R[PPC], A[PPC], Gc[PPC];
+    T R[PPC], A[PPC], Gc[PPC];      // R arrives column-major (accumulate_outer), G leaves row-major
 #pragma unroll
-    for (int e = 0; e < PPC; ++e) { R[e] = RG[i * PPC + e]; A[e] = As[i * PPC + e]; }
+    for (int r = 0; r < NDIM; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < M; ++cc) R[r * M + cc] = RG[i * PPC + cc * NDIM + r];
+    }
+#pragma unroll
+    for (int e = 0; e < PPC; ++e) A[e] = As[i * PPC + e];
     const T h = (T)(1.0 / nsteps), h2 = (T)(0.5 / nsteps / nsteps);
 #pragma unroll
     for (int r = 0; r < NDIM; ++r) {
@@ -866,7 +939,7 @@ static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int b
                           const void* points, const void* trels, void* out, cudaStream_t st,
                           const SampleArgs& sa = SampleArgs())
 {
-    const size_t smem = SMEM ? (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T) : 0;
+    const size_t smem = SMEM ? (size_t)g.n_cells * FwdRec<T, NDIM, SMEM>::kStride * sizeof(T) : 0;
     auto kern = k_forward<T, NDIM, STRICT, SMEM, PPT, SAMPLE>;
     if (smem > 48 * 1024)
         CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -890,7 +963,7 @@ static int forward_t(int flags, const Geom& g, int nsteps, int n_theta, long nP,
                      const void* points, const void* trels, void* out, cudaStream_t st,
                      const SampleArgs* sa = nullptr)
 {
-    const bool smem = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T) <= 160 * 1024;
+    const bool smem = (size_t)g.n_cells * FwdRec<T, NDIM, true>::kStride * sizeof(T) <= 160 * 1024;
     const bool strict = !(flags & kFlagFastMath);
     const int ppt = g_tune_fwd_ppt;
     if (sa != nullptr) {       // fused sampling epilogue
