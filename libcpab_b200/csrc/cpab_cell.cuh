@@ -170,7 +170,7 @@ CPAB_HD int find_cell_1d(double p0, const Geom& g)
 // Literal double replay of cpab_ops.cpp:33-104 for T = float (point widened, widths float) and
 // T = double (everything double).  Used as the last-resort path and as the fp64 check mode.
 template <typename T>
-CPAB_HD_NOINLINE int find_cell_2d_replay(T p0, T p1, const Geom& g)
+CPAB_HD int find_cell_2d_replay_body(T p0, T p1, const Geom& g)
 {
     const bool f32 = sizeof(T) == 4;
     const double qx = p0, qy = p1;
@@ -203,13 +203,16 @@ CPAB_HD_NOINLINE int find_cell_2d_replay(T p0, T p1, const Geom& g)
     return base;
 }
 
+template <typename T>
+CPAB_HD_NOINLINE int find_cell_2d_replay(T p0, T p1, const Geom& g) { return find_cell_2d_replay_body<T>(p0, p1, g); }
+
 // In-domain triangle choice from exact remainders, without division where possible.
 //   x = RN(rx/wx), y = RN(ry/wy) in the reference.  rx*wy and ry*wx are products of two floats and
 //   therefore exact in double; distinct values differ by >= 2^-48 relative, which survives the
 //   rounding of the quotients, so  x<y  <=>  rx*wy < ry*wx  exactly.
 //   1-x<y is decided by the same products when |x+y-1| is clearly non-zero; inside a 2^-40 band the
 //   reference's own divisions are replayed.
-CPAB_HD_NOINLINE int triangle_2d_exact(float rx, float ry, float wx, float wy)
+CPAB_HD int triangle_2d_exact_body(float rx, float ry, float wx, float wy)
 {
     const double a = (double)rx * (double)wy;               // exact
     const double b = (double)ry * (double)wx;               // exact
@@ -226,6 +229,8 @@ CPAB_HD_NOINLINE int triangle_2d_exact(float rx, float ry, float wx, float wy)
     }
     return x_lt_y ? (anti ? 2 : 3) : (anti ? 1 : 0);
 }
+
+CPAB_HD_NOINLINE int triangle_2d_exact(float rx, float ry, float wx, float wy) { return triangle_2d_exact_body(rx, ry, wx, wy); }
 
 // One-sided variant used by the 2-D search: with a multiplier nup >= 1/w and the FFMA rounding
 // *down*, the estimate is floor(p * nup) >= floor(p / w) and exceeds it by at most one (only when
@@ -248,7 +253,10 @@ CPAB_HD void divmod_up(float p, float nup, float w, float magic, float& kf, floa
 
 // Rare path of find_cell_2d: a column/row estimate one too large, a point on or near a diagonal,
 // or a point outside the domain near a corner.
-CPAB_HD_NOINLINE int find_cell_2d_rare(float p0, float p1, float kx, float rx, float ky, float ry, const Geom& g)
+// INLINE selects how the (rarer still) exact sub-paths are reached: by call from code that is itself
+// out of line, inlined where the caller must stay free of calls (see find_cell_try).
+template <bool INLINE>
+CPAB_HD int find_cell_2d_rare_body(float p0, float p1, float kx, float rx, float ky, float ry, const Geom& g)
 {
     if (rx < 0.0f) { kx -= 1.0f; rx += g.w[0]; }
     if (ry < 0.0f) { ky -= 1.0f; ry += g.w[1]; }
@@ -256,15 +264,18 @@ CPAB_HD_NOINLINE int find_cell_2d_rare(float p0, float p1, float kx, float rx, f
     const float d1 = xf - yf, d2 = (1.0f - xf) - yf;
     int tri;
     if (fminf(fabsf(d1), fabsf(d2)) < g.band2) {
-        if (!(p0 > 0.0f) | (p0 >= g.span[0]) | !(p1 > 0.0f) | (p1 >= g.span[1]))
-            return find_cell_2d_replay<float>(p0, p1, g);
-        if ((p0 > g.hi2[0]) | (p1 > g.hi2[1]))             // inside, but clamped for the estimate
-            return find_cell_2d_replay<float>(p0, p1, g);
-        tri = triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
+        // outside the domain, or inside but clamped for the estimate: the reference's own sequence
+        if (!(p0 > 0.0f) | (p0 >= g.span[0]) | !(p1 > 0.0f) | (p1 >= g.span[1]) | (p0 > g.hi2[0]) | (p1 > g.hi2[1]))
+            return INLINE ? find_cell_2d_replay_body<float>(p0, p1, g) : find_cell_2d_replay<float>(p0, p1, g);
+        tri = INLINE ? triangle_2d_exact_body(rx, ry, g.w[0], g.w[1]) : triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
     } else {
         tri = (d1 < 0.0f ? 3 : 0) ^ (d2 < 0.0f ? 1 : 0);
     }
     return 4 * (int)fmaf(ky, g.nf[0], kx) + tri;
+}
+CPAB_HD_NOINLINE int find_cell_2d_rare(float p0, float p1, float kx, float rx, float ky, float ry, const Geom& g)
+{
+    return find_cell_2d_rare_body<false>(p0, p1, kx, rx, ky, ry, g);
 }
 
 // Fast path.  Coordinates are clamped to [0, hi2] (hi2 = a float just below the span): a

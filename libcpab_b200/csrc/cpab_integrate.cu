@@ -21,6 +21,7 @@
 // can exceed 65535).  Loads/stores of the planar [ndim,nP] point arrays are unit-stride per
 // coordinate.  The loop trip count is fixed (nstepsolver), so divergence is confined to the rare
 // exact paths of the cell search.
+#include <atomic>
 #include <string_view>
 #include <type_traits>
 
@@ -277,6 +278,69 @@ __device__ __forceinline__ void sample_vjp(const T* pt, int n, long p, const T* 
     }
 #pragma unroll
     for (int j = 0; j < NDIM; ++j) lam[j] *= (T)(s.S[j] - 1);
+}
+
+// =====================================================================================================
+// Work distribution of the adjoint kernel.
+//
+// The grid is persistent (one CTA per resident slot); CTAs draw work units from a global counter.
+// A unit is a range of points of one theta: `bulk_pts` points while plenty of work remains, and
+// `small_pts` for the last ~2 units per slot, so that every SM runs until the end -- with a static
+// grid of equal CTAs the SMs of a B200 finished up to 14 % apart on BASELINE configs[1]
+// (sm__cycles_active min/max 1169k/1354k; profiles/r01b_*), although every CTA does the same work.
+// (k_forward keeps a static grid: there the per-unit barrier and bookkeeping cost more than the
+// balance gained -- 2.21 vs 2.02 ms on 128 thetas x 512^2.)
+// Units are numbered theta-major: resident CTAs spread over many thetas, which keeps the G
+// reductions of one theta from colliding in L2.
+//
+// Counters live in a small ring of self-resetting slots in module memory (no host memset, no
+// caller-provided buffer, usable under graph capture): the last CTA to leave resets the slot.
+// =====================================================================================================
+struct WorkPlan {
+    unsigned total_bulk, total;      // units of the bulk phase / of both phases
+    int bulk_per_theta, small_per_theta;
+    int bulk_pts, small_pts;
+    long nP_bulk;                    // points [0, nP_bulk) of every theta are bulk units, the rest small ones
+    unsigned slot;                   // index into g_work_ring
+};
+constexpr int kWorkRing = 256;
+__device__ unsigned int g_work_ring[kWorkRing][2];
+
+struct WorkUnit { int theta; long begin, end; };
+
+// All threads of the CTA must call this; returns false when the work is exhausted.
+__device__ __forceinline__ bool next_unit(const WorkPlan& wp, long nP, unsigned* s_work, WorkUnit& u)
+{
+    __syncthreads();                                   // everyone is done with the previous unit
+    if (threadIdx.x == 0) *s_work = atomicAdd(&g_work_ring[wp.slot][0], 1u);
+    __syncthreads();
+    const unsigned w = *s_work;
+    if (w >= wp.total) return false;
+    if (w < wp.total_bulk) {
+        u.theta = (int)(w / (unsigned)wp.bulk_per_theta);
+        const int c = (int)(w - (unsigned)u.theta * (unsigned)wp.bulk_per_theta);
+        u.begin = (long)c * wp.bulk_pts;
+        u.end = u.begin + wp.bulk_pts < wp.nP_bulk ? u.begin + wp.bulk_pts : wp.nP_bulk;
+    } else {
+        const unsigned w2 = w - wp.total_bulk;
+        u.theta = (int)(w2 / (unsigned)wp.small_per_theta);
+        const int c = (int)(w2 - (unsigned)u.theta * (unsigned)wp.small_per_theta);
+        u.begin = wp.nP_bulk + (long)c * wp.small_pts;
+        u.end = u.begin + wp.small_pts < nP ? u.begin + wp.small_pts : nP;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void leave_grid(const WorkPlan& wp)
+{
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(&g_work_ring[wp.slot][1], 1u);
+        if (done == gridDim.x - 1) {                   // every CTA has stopped drawing: recycle the slot
+            g_work_ring[wp.slot][0] = 0;
+            g_work_ring[wp.slot][1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // =====================================================================================================
@@ -594,13 +658,12 @@ template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK, bool SAMPLE>
 __global__ void __launch_bounds__(BLOCK, (BwdOcc<T, NDIM, SEG, BLOCK>::kMinBlocks))
 k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __restrict__ gout,
            T* __restrict__ G, T* __restrict__ dpoints, long nP, int broadcast, int nsteps,
-           const __grid_constant__ Geom g, int chunks, int chunk_pts,
+           const __grid_constant__ Geom g, const __grid_constant__ WorkPlan wp,
            const T* __restrict__ data, const T* __restrict__ gimg, const __grid_constant__ Shape sh)
 {
     constexpr int PPC = Dim<NDIM>::kPpc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int theta = blockIdx.x / chunks;
-    const int chunk = blockIdx.x - theta * chunks;
+    __shared__ unsigned s_work;
     constexpr int WS = StepRec<NDIM>::kStride;
     const int tsize = g.n_cells * PPC;
     const int wsize = g.n_cells * WS;
@@ -615,12 +678,17 @@ k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __re
     int* ct32 = reinterpret_cast<int*>(ct16);
     const bool wide = !SMEM && g.n_cells > 65535;
     CellTable<T, NDIM, SMEM, WS> tab;
+    tab.saddr = SMEM ? (uint32_t)__cvta_generic_to_shared(sW) & 0xffffffu : 0;   // CTA-local offset (no cluster launch: rank bits are 0)
+    int staged = -1;
+    WorkUnit wu;
+    while (next_unit(wp, nP, &s_work, wu)) {
+    const int theta = wu.theta;
+    const long begin = wu.begin, end = wu.end;
     tab.gptr = Ws + (size_t)theta * wsize;
-    tab.saddr = 0;
-    if (SMEM) {
+    if (SMEM && theta != staged) {           // (next_unit synchronised: nobody reads the old table any more)
         stage_block(sW, tab.gptr, wsize);
+        staged = theta;
         __syncthreads();
-        tab.saddr = (uint32_t)__cvta_generic_to_shared(sW) & 0xffffffu;   // CTA-local offset (no cluster launch: rank bits are 0)
     }
     T* Gg = G + (size_t)theta * tsize;
     // keep the base in registers: the flush blocks run divergently, often, and would otherwise
@@ -628,8 +696,6 @@ k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __re
     asm volatile("" : "+l"(Gg));
     const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
     const T* gsrc = gout + (size_t)theta * NDIM * nP;
-    const long begin = (long)chunk * chunk_pts;
-    const long end = begin + chunk_pts < nP ? begin + chunk_pts : nP;
 
     for (long base = begin; base < end; base += BLOCK) {      // warp-uniform trip count
         const long i = base + threadIdx.x;
@@ -733,6 +799,8 @@ k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __re
         }
         flush_runs<T, PPC>(Gg, cur, acc);
     }
+    }   // work units
+    leave_grid(wp);
 }
 
 // Per (theta, cell): the RK2 step record (see step_inc) from A_c = [L | t], and a zeroed R_c block.
@@ -927,6 +995,38 @@ static void pick_chunks(long nP, int n_theta, int block, int ctas_per_sm, int& c
     chunks = (int)((nP + chunk_pts - 1) / chunk_pts);
 }
 
+// Work plan of one launch (see WorkPlan).  Bulk units of `chunk_pts` points (1024 by default:
+// within 1 % of the best size on every BASELINE shape, profiles/r01b_chunk_sweep.txt -- smaller
+// units concentrate the resident CTAs on few thetas and the G reductions of one theta collide in
+// L2, larger ones leave a longer tail), then about two small units per resident CTA.  Problems
+// that cannot fill the chip with bulk units are cut into small ones altogether.
+static std::atomic<unsigned> g_plan_seq{0};
+static WorkPlan plan_work(long nP, int n_theta, int block, int ctas_per_sm, unsigned& grid)
+{
+    WorkPlan wp;
+    const int unit = block > 256 ? block : 256;
+    const long slots = (long)sm_count() * (ctas_per_sm > 0 ? ctas_per_sm : 1);
+    wp.bulk_pts = g_tune_chunk_pts;
+    wp.small_pts = unit;
+    long small_per_theta = 0;
+    if (g_tune_chunk_auto) {
+        small_per_theta = (2 * slots + n_theta - 1) / n_theta;                       // ~2 small units per slot
+        const long all_small = (nP + unit - 1) / unit;
+        if (small_per_theta > all_small || (long)n_theta * ((nP + wp.bulk_pts - 1) / wp.bulk_pts) < slots)
+            small_per_theta = all_small;
+    }
+    long tail_pts = small_per_theta * unit;
+    if (tail_pts > nP) tail_pts = nP;
+    wp.nP_bulk = (nP - tail_pts) / unit * unit;
+    wp.small_per_theta = (int)((nP - wp.nP_bulk + unit - 1) / unit);
+    wp.bulk_per_theta = (int)((wp.nP_bulk + wp.bulk_pts - 1) / wp.bulk_pts);
+    wp.total_bulk = (unsigned)((long)n_theta * wp.bulk_per_theta);
+    wp.total = wp.total_bulk + (unsigned)((long)n_theta * wp.small_per_theta);
+    wp.slot = g_plan_seq.fetch_add(1, std::memory_order_relaxed) % kWorkRing;
+    grid = (unsigned)((long)wp.total < slots ? (long)wp.total : slots);
+    return wp;
+}
+
 struct SampleArgs {       // fused transform_data: images to sample from / to, their geometry
     const void* data = nullptr;
     void* img = nullptr;          // forward: sampled output image
@@ -1045,15 +1145,15 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
     auto launch = [&](auto kern, const SampleArgs& a) -> int {
         if (smem > 48 * 1024)
             CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int chunks, chunk_pts, per_sm = 0;
+        int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
-        pick_chunks(nP, n_theta, BLOCK, per_sm, chunks, chunk_pts);
-        const long long blocks = (long long)n_theta * chunks;
-        if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+        if ((long long)n_theta * ((nP + 255) / 256) > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+        unsigned blocks = 0;
+        const WorkPlan wp = plan_work(nP, n_theta, BLOCK, per_sm, blocks);
         prof_begin(kProfBackward, st);
-        kern<<<(unsigned)blocks, BLOCK, smem, st>>>((const T*)points, (const T*)Ws, (const T*)gout, (T*)G,
-                                                    (T*)dpoints, nP, broadcast, nsteps, g, chunks, chunk_pts,
-                                                    (const T*)a.data, (const T*)a.gimg, a.sh);
+        kern<<<blocks, BLOCK, smem, st>>>((const T*)points, (const T*)Ws, (const T*)gout, (T*)G,
+                                          (T*)dpoints, nP, broadcast, nsteps, g, wp,
+                                          (const T*)a.data, (const T*)a.gimg, a.sh);
         prof_end(kProfBackward, st);
         count_launch();
         return kOk;
