@@ -267,7 +267,15 @@ CPAB_HD int find_cell_2d_rare_body(float p0, float p1, float kx, float rx, float
         // outside the domain, or inside but clamped for the estimate: the reference's own sequence
         if (!(p0 > 0.0f) | (p0 >= g.span[0]) | !(p1 > 0.0f) | (p1 >= g.span[1]) | (p0 > g.hi2[0]) | (p1 > g.hi2[1]))
             return INLINE ? find_cell_2d_replay_body<float>(p0, p1, g) : find_cell_2d_replay<float>(p0, p1, g);
-        tri = INLINE ? triangle_2d_exact_body(rx, ry, g.w[0], g.w[1]) : triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
+        if (rx == ry && g.w[0] == g.w[1]) {
+            // exactly on the main diagonal of a square cell (a uniform_meshgrid commensurate with
+            // the tessellation puts ~2 % of its points there at t = 0): the reference divides the
+            // same operands twice, so x == y and `x < y` is false; 1 - x < x <=> x > 1/2 <=> 2 rx > w,
+            // exact in float32
+            tri = (rx + rx > g.w[0]) ? 1 : 0;
+        } else {
+            tri = INLINE ? triangle_2d_exact_body(rx, ry, g.w[0], g.w[1]) : triangle_2d_exact(rx, ry, g.w[0], g.w[1]);
+        }
     } else {
         tri = (d1 < 0.0f ? 3 : 0) ^ (d2 < 0.0f ? 1 : 0);
     }
@@ -439,6 +447,26 @@ template <int NDIM> CPAB_HD bool find_cell_try(const float* p, const Geom& g, fl
     cell = find_cell<NDIM, float>(p, g);
     return false;
 }
+// Second half for the kernels' slow step: `est` carries the estimates of find_cell_try.
+struct CellEst { float kx, rx, ky, ry; };
+template <int NDIM> CPAB_HD bool find_cell_try(const float* p, const Geom& g, float magic, int& cell, CellEst& est)
+{
+    if (NDIM == 2) return find_cell_2d_fast(p[0], p[1], g, magic, cell, est.kx, est.rx, est.ky, est.ry);
+    cell = find_cell<NDIM, float>(p, g);
+    return false;
+}
+template <int NDIM> CPAB_HD int find_cell_finish(const float* p, const Geom& g, const CellEst& est)
+{
+    if (NDIM == 2) return find_cell_2d_rare(p[0], p[1], est.kx, est.rx, est.ky, est.ry, g);
+    return find_cell<NDIM, float>(p, g);
+}
+template <int NDIM> CPAB_HD bool find_cell_try(const double* p, const Geom& g, float, int& cell, CellEst&)
+{
+    cell = find_cell<NDIM, double>(p, g);
+    return false;
+}
+template <int NDIM> CPAB_HD int find_cell_finish(const double* p, const Geom& g, const CellEst&) { return find_cell<NDIM, double>(p, g); }
+
 template <int NDIM> CPAB_HD bool find_cell_try(const double* p, const Geom& g, float, int& cell)
 {
     cell = find_cell<NDIM, double>(p, g);

@@ -443,19 +443,22 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
             }
         }
         while (kHasRarePath) {
+            int c[PPT];
+            bool rare[PPT];
+            CellEst est[PPT];
 #pragma unroll 2
             for (; s < nsteps; ++s) {
-                int c[PPT];
-                bool rare = false;
+                bool any = false;
 #pragma unroll
-                for (int u = 0; u < PPT; ++u) rare |= find_cell_try<NDIM>(p[u], g, magic, c[u]);
-                if (__any_sync(0xffffffffu, rare)) break;
+                for (int u = 0; u < PPT; ++u) any |= (rare[u] = find_cell_try<NDIM>(p[u], g, magic, c[u], est[u]));
+                if (__any_sync(0xffffffffu, any)) break;
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) advance(u, c[u]);
             }
             if (s >= nsteps) break;
+            // slow step: the lanes that asked for it finish their search from the estimates
 #pragma unroll
-            for (int u = 0; u < PPT; ++u) advance(u, find_cell<NDIM>(p[u], g));
+            for (int u = 0; u < PPT; ++u) advance(u, rare[u] ? find_cell_finish<NDIM>(p[u], g, est[u]) : c[u]);
             ++s;
         }
 #pragma unroll
