@@ -358,6 +358,28 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     interp_prof = _lib.profile_read("interp_fwd")
     _lib.profile_enable(False)
+    # ... and once on an HBM-resident problem of the same kind (128 images of 512^2 for 2-D; the
+    # workload's own shape is a 20-30 us launch, too short to reach any bandwidth)
+    interp_big = None
+    if ndim == 2 and rank == 0:
+        with torch.no_grad():
+            big = [512, 512]
+            th2 = torch.randn(128, T.params.d, device=dev)
+            gt2 = T.transform_grid(T.uniform_meshgrid(big), th2)
+            d2 = torch.rand(128, C, *big, device=dev)
+            ops.interpolate_forward(d2, gt2, big)
+            torch.cuda.synchronize()
+            _lib.profile_enable(True)
+            for _ in range(5):
+                flush.add_(1.0)
+                ops.interpolate_forward(d2, gt2, big)
+            torch.cuda.synchronize()
+            b_ms, b_n = _lib.profile_read("interp_fwd")
+            _lib.profile_enable(False)
+            b_bytes = 128 * big[0] * big[1] * (4 * ndim + 8 * C)
+            interp_big = {"shape": "128 x %d x 512 x 512" % C, "ms_per_launch": b_ms / max(b_n, 1),
+                          "achieved": b_bytes / (b_ms / max(b_n, 1) * 1e-3) / 1e9 if b_n else None, "unit": "GB/s"}
+            del th2, gt2, d2
 
     barrier()
     # two passes of K pipelined steps, the faster one is reported (a pass shares PCIe and the host
@@ -408,6 +430,9 @@ def run_gpu_arm(args):
                 "(inside the step the sampler may run fused into the integration kernels)",
     }
     roofline_interp["frac"] = roofline_interp["achieved"] / roofline_interp["peak"] if roofline_interp["achieved"] else None
+    if interp_big and interp_big["achieved"]:
+        interp_big["frac"] = interp_big["achieved"] / roofline_interp["peak"]
+        roofline_interp["hbm_sized"] = interp_big
     roofline_fwd = {
         "kernel": "k_forward", "bound": "fp32",
         "achieved": pairs_rank * F_FWD[ndim] / (fwd_ms / max(fwd_n, 1) * 1e-3) / 1e12 if fwd_n else None,

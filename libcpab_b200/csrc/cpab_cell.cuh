@@ -391,14 +391,31 @@ CPAB_HD_NOINLINE int find_cell_3d_replay(T q0, T q1, T q2, const Geom& g)
     return cell;
 }
 
-CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g)
+// Fast path; returns true when the point lies within the guard band of a separating plane and
+// needs the exact replay (`cell` is then not meaningful).  The outside-the-box push stays inline:
+// zero-boundary flows park points on the faces, where they wobble an ulp outside on many steps.
+CPAB_HD bool find_cell_3d_fast(float p0, float p1, float p2, const Geom& g, int& cell, float* q)
 {
     float q0 = p0, q1 = p1, q2 = p2;
     if (q0 < 0.0f || q0 > 1.0f || q1 < 0.0f || q1 > 1.0f)       // sic: z is not tested (:119)
         push_inside_3d<float>(q0, q1, q2, g.w[0], g.w[1], g.w[2]);
+    q[0] = q0; q[1] = q1; q[2] = q2;
     float kx, ky, kz, rx, ry, rz;
-    divmod_exact(fminf(g.hi3[0], fmaxf(0.0f, q0)), g.nf[0], g.w[0], kx, rx);
-    divmod_exact(fminf(g.hi3[1], fmaxf(0.0f, q1)), g.nf[1], g.w[1], ky, ry);
+    const float c0 = fminf(g.hi3[0], fmaxf(0.0f, q0)), c1 = fminf(g.hi3[1], fmaxf(0.0f, q1));
+#if defined(__CUDA_ARCH__)
+    {   // x and y as one packed sequence (cpab_f32x2.cuh); per lane identical to divmod_exact
+        const F2 pc = pk(c0, c1), mg = bc(12582912.0f);
+        const F2 kf = sub2(fma2(pc, pk(g.nf[0], g.nf[1]), mg), mg);
+        const F2 r = fma2(kf, pk(-g.w[0], -g.w[1]), pc);
+        unpk(kf, kx, ky);
+        unpk(r, rx, ry);
+        if (rx < 0.0f) { kx -= 1.0f; rx += g.w[0]; }
+        if (ry < 0.0f) { ky -= 1.0f; ry += g.w[1]; }
+    }
+#else
+    divmod_exact(c0, g.nf[0], g.w[0], kx, rx);
+    divmod_exact(c1, g.nf[1], g.w[1], ky, ry);
+#endif
     divmod_exact(fminf(g.hi3[2], fmaxf(0.0f, q2)), g.nf[2], g.w[2], kz, rz);
     kx = fminf(kx, g.nm1[0]);
     ky = fminf(ky, g.nm1[1]);
@@ -411,9 +428,17 @@ CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g)
     const float s = x + y, u = y - x;
     const float t1 = z - s, t2 = (s + z) - 2.0f, t3 = u - z, t4 = -u - z;
     const float nearest = fminf(fminf(fabsf(t1), fabsf(t2)), fminf(fabsf(t3), fabsf(t4)));
-    if (nearest < 4e-6f) return find_cell_3d_replay<float>(q0, q1, q2, g);
     const int tet = (t1 >= 0.0f) ? 1 : (t2 >= 0.0f) ? 2 : (t3 >= 0.0f) ? 3 : (t4 >= 0.0f) ? 4 : 0;
-    return 5 * cube + tet;
+    cell = 5 * cube + tet;
+    return nearest < 4e-6f;
+}
+
+CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g)
+{
+    int cell;
+    float q[3];
+    if (find_cell_3d_fast(p0, p1, p2, g, cell, q)) return find_cell_3d_replay<float>(q[0], q[1], q[2], g);
+    return cell;
 }
 
 CPAB_HD int find_cell_3d(double p0, double p1, double p2, const Geom& g)
@@ -452,12 +477,14 @@ struct CellEst { float kx, rx, ky, ry; };
 template <int NDIM> CPAB_HD bool find_cell_try(const float* p, const Geom& g, float magic, int& cell, CellEst& est)
 {
     if (NDIM == 2) return find_cell_2d_fast(p[0], p[1], g, magic, cell, est.kx, est.rx, est.ky, est.ry);
+    if (NDIM == 3) { float q[3]; return find_cell_3d_fast(p[0], p[1], p[2], g, cell, q); }
     cell = find_cell<NDIM, float>(p, g);
     return false;
 }
 template <int NDIM> CPAB_HD int find_cell_finish(const float* p, const Geom& g, const CellEst& est)
 {
     if (NDIM == 2) return find_cell_2d_rare(p[0], p[1], est.kx, est.rx, est.ky, est.ry, g);
+    if (NDIM == 3) return find_cell<3, float>(p, g);
     return find_cell<NDIM, float>(p, g);
 }
 template <int NDIM> CPAB_HD bool find_cell_try(const double* p, const Geom& g, float, int& cell, CellEst&)

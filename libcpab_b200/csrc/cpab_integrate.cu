@@ -423,6 +423,20 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
                     p[u][0] = fmaf(a[0], x, fmaf(a[1], y, t[0]));
                     p[u][1] = fmaf(a[2], x, fmaf(a[3], y, t[1]));
                 }
+            } else if constexpr (NDIM == 3 && sizeof(T) == 4 && STRICT) {
+                // row r = (a_r0 a_r1 | a_r2 a_r3): products as two packed multiplies with
+                // (p0 p1) and (p2 1), sums scalar and separately rounded, in the reference's order
+                float a[PPC];
+                tab.load(c, a);
+                const F2 P01 = pk(p[u][0], p[u][1]), P2 = pk(p[u][2], 1.0f);
+                float q[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const F2 m0 = mul2(pk(a[4 * r], a[4 * r + 1]), P01), m1 = mul2(pk(a[4 * r + 2], a[4 * r + 3]), P2);
+                    q[r] = __fadd_rn(__fadd_rn(__fadd_rn(lo(m0), hi(m0)), lo(m1)), hi(m1));
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) p[u][j] = q[j];
             } else {
                 T a[PPC], q[NDIM];
                 tab.load(c, a);
@@ -434,7 +448,7 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
         // The inner loop runs fast-path steps until some lane of the warp needs the complete cell
         // search (a point on a diagonal, a corner outside the domain...; ~1e-5 per point and
         // step); that one step is then done for the whole warp below and the loop resumes.
-        constexpr bool kHasRarePath = NDIM == 2 && sizeof(T) == 4;   // see find_cell_try
+        constexpr bool kHasRarePath = NDIM >= 2 && sizeof(T) == 4;   // see find_cell_try
         int s = 0;
         if (!kHasRarePath) {
             for (; s < nsteps; ++s) {
