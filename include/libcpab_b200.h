@@ -11,8 +11,8 @@
  * Conventions
  *   - All data pointers are DEVICE pointers to contiguous row-major arrays of `dtype`
  *     (CPAB_F32 = float, CPAB_F64 = double "check mode") on the current device.
- *   - Every entry point is safe under CUDA-graph stream capture (no host synchronisation,
- *     allocation or memset).  The only state inside the library is a 2 KB ring of self-resetting
+ *   - Every entry point is safe under CUDA-graph stream capture (no host synchronisation
+ *     or allocation).  The only state inside the library is a 2 KB ring of self-resetting
  *     work counters in module memory, from which the adjoint kernel draws its work units; a launch
  *     takes the next of 256 slots, so up to 256 launches may be in flight on different streams
  *     (a captured graph keeps its slot: do not replay one graph concurrently with itself).
