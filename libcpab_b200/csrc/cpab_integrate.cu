@@ -905,38 +905,53 @@ k_r_to_g(T* __restrict__ RG, const T* __restrict__ As, long n_blocks, int nsteps
 }
 
 // dtheta[t][k] = sum_e G[t][e] * B[e][k]      (G [n_theta,D], B [D,d] row-major, dtheta [n_theta,d])
+// A skinny GEMM (d ~ 50-250, D up to a few thousand, n_theta from 16 to 65536): grid = theta tiles
+// of TT x chunks of `ek` rows of B.  With few thetas the work is split along e (split-K) so that
+// the chip is filled -- 16 thetas x D = 3840 ran on 4 CTAs for 0.57 ms before -- and the partial
+// sums are reduced into a zeroed dtheta with native float atomics.  Four independent loads of B
+// are in flight per thread; G tiles are read through shared memory.
 template <typename T, int TT>
 __global__ void __launch_bounds__(128)
 k_grad_epilogue(const T* __restrict__ G, const T* __restrict__ B, T* __restrict__ dtheta,
-                int n_theta, int D, int d)
+                int n_theta, int D, int d, int ek, int split)
 {
     constexpr int TILE = 256;
     __shared__ T sG[TT][TILE];
     const int t0 = blockIdx.x * TT;
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
-    T acc[TT];
+    const int e0 = blockIdx.y * ek;
+    const int n = D - e0 < ek ? D - e0 : ek;
+    for (int x = threadIdx.x; x < TT * TILE; x += blockDim.x) {
+        const int u = x / TILE, e = x - u * TILE;
+        sG[u][e] = (t0 + u < n_theta && e < n) ? G[(size_t)(t0 + u) * D + e0 + e] : (T)0;
+    }
+    __syncthreads();
+    const T* Bp = B + (size_t)e0 * d;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        T acc[TT];
 #pragma unroll
-    for (int u = 0; u < TT; ++u) acc[u] = 0;
-    for (int e0 = 0; e0 < D; e0 += TILE) {
-        const int n = D - e0 < TILE ? D - e0 : TILE;
-        __syncthreads();
-        for (int x = threadIdx.x; x < TT * TILE; x += blockDim.x) {
-            const int u = x / TILE, e = x - u * TILE;
-            sG[u][e] = (t0 + u < n_theta && e < n) ? G[(size_t)(t0 + u) * D + e0 + e] : (T)0;
+        for (int u = 0; u < TT; ++u) acc[u] = 0;
+        int e = 0;
+        for (; e + 4 <= n; e += 4) {
+            T bv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = __ldg(Bp + (size_t)(e + j) * d + k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int u = 0; u < TT; ++u) acc[u] = Num<T>::fma(sG[u][e + j], bv[j], acc[u]);
         }
-        __syncthreads();
-        if (k < d) {
-            for (int e = 0; e < n; ++e) {
-                const T b = __ldg(B + (size_t)(e0 + e) * d + k);
+        for (; e < n; ++e) {
+            const T bv = __ldg(Bp + (size_t)e * d + k);
 #pragma unroll
-                for (int u = 0; u < TT; ++u) acc[u] = Num<T>::fma(sG[u][e], b, acc[u]);
+            for (int u = 0; u < TT; ++u) acc[u] = Num<T>::fma(sG[u][e], bv, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < TT; ++u) {
+            if (t0 + u < n_theta) {
+                T* dst = dtheta + (size_t)(t0 + u) * d + k;
+                if (split) Num<T>::atomic_add(dst, acc[u]); else *dst = acc[u];
             }
         }
-    }
-    if (k < d) {
-#pragma unroll
-        for (int u = 0; u < TT; ++u)
-            if (t0 + u < n_theta) dtheta[(size_t)(t0 + u) * d + k] = acc[u];
     }
 }
 
@@ -1237,10 +1252,26 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
         CPAB_CUDA_OK(cudaGetLastError());
         count_launch();
     }
-    constexpr int TT = 8;
-    dim3 grid((unsigned)((n_theta + TT - 1) / TT), (unsigned)((d + 127) / 128));
+    return launch_grad_epilogue(sizeof(T) == 4 ? kF32 : kF64, ws, basis, dtheta, n_theta, D, d, st);
+}
+
+template <typename T>
+static int grad_epilogue_t(const void* G, const void* basis, void* dtheta, int n_theta, int D, int d, cudaStream_t st)
+{
+    // theta tile and e-chunk: as large as possible (B is re-read once per theta tile) while the
+    // grid still covers the chip about twice
+    const long want = 2L * sm_count();
+    int tt = 8, ek = 256;
+    auto ctas = [&]() { return (long)((n_theta + tt - 1) / tt) * ((D + ek - 1) / ek); };
+    while (tt > 1 && ctas() < want) tt /= 2;
+    while (ek > 32 && ctas() < want) ek /= 2;
+    const int split = (D + ek - 1) / ek > 1;
+    if (split) CPAB_CUDA_OK(cudaMemsetAsync(dtheta, 0, (size_t)n_theta * d * sizeof(T), st));
+    dim3 grid((unsigned)((n_theta + tt - 1) / tt), (unsigned)((D + ek - 1) / ek));
     prof_begin(kProfEpilogue, st);
-    k_grad_epilogue<T, TT><<<grid, 128, 0, st>>>((const T*)ws, (const T*)basis, (T*)dtheta, n_theta, D, d);
+#define EPI(TT) k_grad_epilogue<T, TT><<<grid, 128, 0, st>>>((const T*)G, (const T*)basis, (T*)dtheta, n_theta, D, d, ek, split)
+    if (tt == 8) EPI(8); else if (tt == 4) EPI(4); else if (tt == 2) EPI(2); else EPI(1);
+#undef EPI
     prof_end(kProfEpilogue, st);
     count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
@@ -1251,15 +1282,9 @@ int launch_grad_epilogue(int dtype, const void* G, const void* basis, void* dthe
                          int d, cudaStream_t st)
 {
     if (n_theta == 0 || d == 0) return kOk;
-    constexpr int TT = 8;
-    dim3 grid((unsigned)((n_theta + TT - 1) / TT), (unsigned)((d + 127) / 128));
-    prof_begin(kProfEpilogue, st);
-    if (dtype == kF32) k_grad_epilogue<float, TT><<<grid, 128, 0, st>>>((const float*)G, (const float*)basis, (float*)dtheta, n_theta, D, d);
-    else k_grad_epilogue<double, TT><<<grid, 128, 0, st>>>((const double*)G, (const double*)basis, (double*)dtheta, n_theta, D, d);
-    prof_end(kProfEpilogue, st);
-    count_launch();
-    CPAB_CUDA_OK(cudaGetLastError());
-    return kOk;
+    if ((long)((n_theta + 7) / 8) > 0x7fffffffL || (D + 31) / 32 > 65535) { set_error("gradient epilogue: grid too large"); return kErrUnsupported; }
+    return dtype == kF32 ? grad_epilogue_t<float>(G, basis, dtheta, n_theta, D, d, st)
+                         : grad_epilogue_t<double>(G, basis, dtheta, n_theta, D, d, st);
 }
 
 int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int d, long nP,

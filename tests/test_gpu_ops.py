@@ -272,6 +272,35 @@ def test_backward_other_step_counts_and_tuning():
             assert_grad_parity(dth.cpu().numpy(), ref, F32_TOL)
 
 
+@pytest.mark.parametrize("nc,n_theta,nP", [([7], 1, 1), ([7], 3, 31), ([50], 700, 257), ([3, 3], 1, 255),
+                                           ([3, 3], 5, 1000), ([4, 3], 2, 5000), ([2, 2, 2], 3, 513)])
+def test_backward_ragged_sizes_through_the_work_units(nc, n_theta, nP):
+    """Work units of the adjoint kernel (bulk units, small tail units, partial last units, more
+    or fewer units than resident CTAs): float64 check mode against the oracle, so that no cell
+    flip can hide an indexing error."""
+    from libcpab_b200 import _lib, ops
+    rng = np.random.default_rng(nP + n_theta)
+    ndim = len(nc)
+    nC = int({1: 1, 2: 4, 3: 5}[ndim] * np.prod(nc))
+    d = 4
+    B = rng.normal(size=(nC * ndim * (ndim + 1), d)) * 0.4
+    theta = rng.normal(size=(n_theta, d))
+    As = O.theta_to_affine(B, theta, nc, dtype=np.float64)
+    pts = rng.uniform(0.0, 1.0, (ndim, nP))
+    gout = rng.normal(size=(n_theta, ndim, nP))
+    ref = O.theta_grad(pts, As, bs_of(B, nc, np.float64), gout, nc, 50, threads=8)
+    for chunk in (None, 256, 4096):
+        try:
+            if chunk:
+                _lib.set_tuning("chunk_pts", chunk)
+            dth, dpts = ops.backward_theta(dev(pts), dev(As), dev(B), dev(gout), nc, 50, want_dpoints=True)
+        finally:
+            _lib.set_tuning("chunk_pts", 1024)
+            _lib.set_tuning("chunk_auto", 1)
+        assert rel_err(dth.cpu().numpy(), ref) < 1e-9, chunk
+        assert dpts.shape == (n_theta, ndim, nP) and bool(torch.isfinite(dpts).all())
+
+
 # --------------------------------------------------------------------------------- interpolation
 @pytest.mark.parametrize("name", [n for n in golden_cases() if "data" in load_golden(n).files])
 def test_interpolate_forward_bit_identical(name):
