@@ -390,7 +390,10 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
             stage_block(sT, tab.gptr, tsize);
         }
         __syncthreads();
-        tab.saddr = (uint32_t)__cvta_generic_to_shared(sT) & 0xffffffu;   // CTA-local offset (no cluster launch: rank bits are 0)
+        // CTA-local offset (no cluster launch: rank bits are 0).  `nsteps >> 30` is a zero ptxas
+        // does not know: without it the base is rebuilt in the loop (S2R, MOV, LEA, LOP3 per step)
+        // wherever the mask does not fold to a constant.
+        tab.saddr = ((uint32_t)__cvta_generic_to_shared(sT) & 0xffffffu) + (uint32_t)(nsteps >> 30);
     }
     const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
     T* dst = out + (size_t)theta * NDIM * nP;
@@ -424,16 +427,17 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
                     p[u][1] = fmaf(a[2], x, fmaf(a[3], y, t[1]));
                 }
             } else if constexpr (NDIM == 3 && sizeof(T) == 4 && STRICT) {
-                // row r = (a_r0 a_r1 | a_r2 a_r3): products as two packed multiplies with
-                // (p0 p1) and (p2 1), sums scalar and separately rounded, in the reference's order
+                // row r = (a_r0 a_r1 | a_r2 a_r3): the first two products as one packed multiply with
+                // (p0 p1), sums scalar and separately rounded, in the reference's order
                 float a[PPC];
                 tab.load(c, a);
-                const F2 P01 = pk(p[u][0], p[u][1]), P2 = pk(p[u][2], 1.0f);
+                const F2 P01 = pk(p[u][0], p[u][1]);
                 float q[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const F2 m0 = mul2(pk(a[4 * r], a[4 * r + 1]), P01), m1 = mul2(pk(a[4 * r + 2], a[4 * r + 3]), P2);
-                    q[r] = __fadd_rn(__fadd_rn(__fadd_rn(lo(m0), hi(m0)), lo(m1)), hi(m1));
+                    const F2 m0 = mul2(pk(a[4 * r], a[4 * r + 1]), P01);
+                    const float m2 = __fmul_rn(a[4 * r + 2], p[u][2]);
+                    q[r] = __fadd_rn(__fadd_rn(__fadd_rn(lo(m0), hi(m0)), m2), a[4 * r + 3]);
                 }
 #pragma unroll
                 for (int j = 0; j < 3; ++j) p[u][j] = q[j];
