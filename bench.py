@@ -63,7 +63,7 @@ DEFAULT_WORKLOAD = "cfg2_2d_t3x3_b64_256x256"
 # capture of this very command (profiles/r01_ncu_bench_cfg2_summary.txt); null for workloads
 # that were not captured
 NCU_TRAFFIC_BYTES = {     # profiles/r01b_ncu_bench_cfg2_summary.txt (fused transform_data kernels)
-    "cfg2_2d_t3x3_b64_256x256": {"k_backward": 70.44e6, "k_forward": 18.64e6, "k_interp_fwd": 51.54e6},
+    "cfg2_2d_t3x3_b64_256x256": {"k_backward": 70.83e6, "k_forward": 19.39e6, "k_interp_fwd": 51.54e6},
 }
 
 

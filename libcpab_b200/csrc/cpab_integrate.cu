@@ -308,14 +308,9 @@ __device__ unsigned int g_work_ring[kWorkRing][2];
 
 struct WorkUnit { int theta; long begin, end; };
 
-// All threads of the CTA must call this; returns false when the work is exhausted.
-__device__ __forceinline__ bool next_unit(const WorkPlan& wp, long nP, unsigned* s_work, WorkUnit& u)
+// Unit number -> (theta, point range): bulk units of all thetas first, then the small ones.
+__device__ __forceinline__ void unit_of(const WorkPlan& wp, unsigned w, long nP, WorkUnit& u)
 {
-    __syncthreads();                                   // everyone is done with the previous unit
-    if (threadIdx.x == 0) *s_work = atomicAdd(&g_work_ring[wp.slot][0], 1u);
-    __syncthreads();
-    const unsigned w = *s_work;
-    if (w >= wp.total) return false;
     if (w < wp.total_bulk) {
         u.theta = (int)(w / (unsigned)wp.bulk_per_theta);
         const int c = (int)(w - (unsigned)u.theta * (unsigned)wp.bulk_per_theta);
@@ -328,6 +323,17 @@ __device__ __forceinline__ bool next_unit(const WorkPlan& wp, long nP, unsigned*
         u.begin = wp.nP_bulk + (long)c * wp.small_pts;
         u.end = u.begin + wp.small_pts < nP ? u.begin + wp.small_pts : nP;
     }
+}
+
+// All threads of the CTA must call this; returns false when the work is exhausted.
+__device__ __forceinline__ bool next_unit(const WorkPlan& wp, long nP, unsigned* s_work, WorkUnit& u)
+{
+    __syncthreads();                                   // everyone is done with the previous unit
+    if (threadIdx.x == 0) *s_work = atomicAdd(&g_work_ring[wp.slot][0], 1u);
+    __syncthreads();
+    const unsigned w = *s_work;
+    if (w >= wp.total) return false;
+    unit_of(wp, w, nP, u);
     return true;
 }
 
@@ -364,14 +370,17 @@ __global__ void __launch_bounds__(256) k_findcellidx(const T* __restrict__ pts, 
 template <typename T, int NDIM, bool STRICT, bool SMEM, int PPT, bool SAMPLE>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 4 : 1))
 k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restrict__ out, long nP,
-          int broadcast, int nsteps, const __grid_constant__ Geom g, int chunks, int chunk_pts,
+          int broadcast, int nsteps, const __grid_constant__ Geom g, const __grid_constant__ WorkPlan wp,
           const T* __restrict__ data, T* __restrict__ img, const __grid_constant__ Shape sh)
 {
     constexpr int PPC = Dim<NDIM>::kPpc;
     constexpr bool kPacked = FwdRec<T, NDIM, SMEM>::kPacked;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int theta = blockIdx.x / chunks;
-    const int chunk = blockIdx.x - theta * chunks;
+    // static grid, one CTA per work unit (1024 points of one theta; 256 when the whole problem
+    // would not fill the chip otherwise)
+    WorkUnit wu;
+    unit_of(wp, blockIdx.x, nP, wu);
+    const int theta = wu.theta;
     const int tsize = g.n_cells * PPC;
     CellTable<T, NDIM, SMEM, FwdRec<T, NDIM, SMEM>::kStride> tab;
     tab.gptr = trels + (size_t)theta * tsize;
@@ -397,8 +406,7 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
     }
     const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
     T* dst = out + (size_t)theta * NDIM * nP;
-    const long begin = (long)chunk * chunk_pts;
-    const long end = begin + chunk_pts < nP ? begin + chunk_pts : nP;
+    const long begin = wu.begin, end = wu.end;
 
     const float magic = 12582912.0f;     // 1.5 * 2^23, rounding constant of the 2-D cell search
     for (long b0 = begin; b0 < end; b0 += (long)blockDim.x * PPT) {      // warp-uniform trip count
@@ -1012,32 +1020,13 @@ static int sm_count()
     return sms;
 }
 
-// Points of one theta handled by one CTA.  Measured on one B200 (profiles/r01b_chunk_sweep.txt):
-// 1024 is within 1 % of the best size on every BASELINE shape -- smaller chunks concentrate the
-// resident CTAs on few thetas (the G reductions of one theta then collide in L2: 2-D [3,3]
-// backward 0.71 ms at 1024, 0.86 at 512, 1.31 at 256), larger ones quantise small problems into
-// few waves (0.83 ms at 4096).  Problems that cannot fill the chip at 1024 are cut finer.
-static void pick_chunks(long nP, int n_theta, int block, int ctas_per_sm, int& chunks, int& chunk_pts)
-{
-    const int unit = block > 256 ? block : 256;
-    chunk_pts = g_tune_chunk_pts;
-    if (g_tune_chunk_auto && ctas_per_sm > 0) {
-        const long slots = (long)sm_count() * ctas_per_sm;
-        while (chunk_pts / 2 >= unit && (chunk_pts / 2) % unit == 0 &&
-               (long)n_theta * ((nP + chunk_pts - 1) / chunk_pts) < slots / 2)
-            chunk_pts /= 2;
-    }
-    if (nP < chunk_pts) chunk_pts = (int)((nP + unit - 1) / unit * unit);
-    chunks = (int)((nP + chunk_pts - 1) / chunk_pts);
-}
-
 // Work plan of one launch (see WorkPlan).  Bulk units of `chunk_pts` points (1024 by default:
 // within 1 % of the best size on every BASELINE shape, profiles/r01b_chunk_sweep.txt -- smaller
 // units concentrate the resident CTAs on few thetas and the G reductions of one theta collide in
 // L2, larger ones leave a longer tail), then about two small units per resident CTA.  Problems
 // that cannot fill the chip with bulk units are cut into small ones altogether.
 static std::atomic<unsigned> g_plan_seq{0};
-static WorkPlan plan_work(long nP, int n_theta, int block, int ctas_per_sm, unsigned& grid)
+static WorkPlan plan_work(long nP, int n_theta, int block, int ctas_per_sm, unsigned& grid, bool counter = true)
 {
     WorkPlan wp;
     const int unit = block > 256 ? block : 256;
@@ -1046,8 +1035,11 @@ static WorkPlan plan_work(long nP, int n_theta, int block, int ctas_per_sm, unsi
     wp.small_pts = unit;
     long small_per_theta = 0;
     if (g_tune_chunk_auto) {
-        small_per_theta = (2 * slots + n_theta - 1) / n_theta;                       // ~2 small units per slot
         const long all_small = (nP + unit - 1) / unit;
+        // the tail pays for itself only when units are drawn from the counter (measured: +6 % for
+        // k_backward on configs[1], nothing for the static grid of k_forward), and not when there
+        // are so many thetas that one small unit each is already a large share of the work
+        if (counter && (long)n_theta <= 2 * slots) small_per_theta = (2 * slots + n_theta - 1) / n_theta;
         if (small_per_theta > all_small || (long)n_theta * ((nP + wp.bulk_pts - 1) / wp.bulk_pts) < slots)
             small_per_theta = all_small;
     }
@@ -1058,7 +1050,7 @@ static WorkPlan plan_work(long nP, int n_theta, int block, int ctas_per_sm, unsi
     wp.bulk_per_theta = (int)((wp.nP_bulk + wp.bulk_pts - 1) / wp.bulk_pts);
     wp.total_bulk = (unsigned)((long)n_theta * wp.bulk_per_theta);
     wp.total = wp.total_bulk + (unsigned)((long)n_theta * wp.small_per_theta);
-    wp.slot = g_plan_seq.fetch_add(1, std::memory_order_relaxed) % kWorkRing;
+    wp.slot = counter ? g_plan_seq.fetch_add(1, std::memory_order_relaxed) % kWorkRing : 0;
     grid = (unsigned)((long)wp.total < slots ? (long)wp.total : slots);
     return wp;
 }
@@ -1079,15 +1071,15 @@ static int forward_launch(const Geom& g, int nsteps, int n_theta, long nP, int b
     auto kern = k_forward<T, NDIM, STRICT, SMEM, PPT, SAMPLE>;
     if (smem > 48 * 1024)
         CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int chunks, chunk_pts, per_sm = 0;
+    int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
-    pick_chunks(nP, n_theta, 256, per_sm, chunks, chunk_pts);
-    const long long blocks = (long long)n_theta * chunks;
-    if (blocks > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+    if ((long long)n_theta * ((nP + 255) / 256) > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+    unsigned slots_grid = 0;
+    const WorkPlan wp = plan_work(nP, n_theta, 256, per_sm, slots_grid, false);
     prof_begin(kProfForward, st);
-    kern<<<(unsigned)blocks, 256, smem, st>>>((const T*)points, (const T*)trels, (T*)out, nP,
-                                              broadcast, nsteps, g, chunks, chunk_pts,
-                                              (const T*)sa.data, (T*)sa.img, sa.sh);
+    kern<<<wp.total, 256, smem, st>>>((const T*)points, (const T*)trels, (T*)out, nP,
+                                      broadcast, nsteps, g, wp,
+                                      (const T*)sa.data, (T*)sa.img, sa.sh);
     prof_end(kProfForward, st);
     count_launch();
     CPAB_CUDA_OK(cudaGetLastError());
