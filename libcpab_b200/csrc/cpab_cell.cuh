@@ -8,7 +8,9 @@
 //     fmod is exact, so the reference's column index is floor_exact(p / w) and its remainder is
 //     p - k*w, both of which a single FP32 FMA delivers exactly: estimate k with one FFMA against
 //     a rounding constant, form r = fma(-k, w, p) (exact: r is a multiple of ulp(w) below 2^24
-//     ulps), fix the estimate by the sign of r.  No division, no conversion instruction.
+//     ulps), fix the estimate by the sign of r.  No division, no conversion instruction.  (2-D uses
+//     a one-sided estimate -- FFMA rounded down with a multiplier >= 1/w -- whose rare miss joins
+//     the guard-band branch, and runs both axes as packed FP32; see divmod_up.)
 //   * The triangle / tetrahedron tests compare local coordinates r/w.  They are evaluated in FP32
 //     with a guard band; only a point within the band of a diagonal (or in a corner region outside
 //     the domain) drops to an exact path.  In 2-D the exact path is still division-free (products

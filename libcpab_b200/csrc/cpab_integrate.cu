@@ -11,16 +11,19 @@
 //                     op-level parity; d-fold redundant by construction)
 //   k_backward        the same RK2 discretisation restated as an adjoint sweep: one pass per
 //                     (point,theta) instead of one per (point,theta,k); accumulates
-//                     G[theta][cell] and never materialises the Jacobian.  Together with
+//                     R[theta][cell] and never materialises the Jacobian.  Together with
+//                     k_prepare_backward (per-cell RK2 step records), k_r_to_g and
 //                     k_grad_epilogue (dtheta = G . B) it replaces cpab_ops.cu:390-697 AND the
 //                     contraction libcpab/pytorch/transformer.py:201.
 //
-// Design notes (B200): one thread owns one (point,theta) trajectory; a CTA works on one theta so
-// that theta's per-cell matrices are staged ONCE in shared memory (2-D [10,10]: 9.6 KB) and every
-// step's gather is a shared-memory read; grid = n_theta x point-chunks, linearised in x (n_theta
-// can exceed 65535).  Loads/stores of the planar [ndim,nP] point arrays are unit-stride per
+// Design notes (B200): one thread owns one (point,theta) trajectory; a CTA works on one theta at a
+// time so that theta's per-cell records are staged in shared memory and every step's gather is a
+// shared-memory read.  k_forward: static grid of n_theta x 1024-point units; its step loop holds
+// no call (the warp votes and leaves the loop when a lane needs the complete cell search).
+// k_backward: persistent grid, units drawn from a counter (WorkPlan).  2-D arithmetic is packed
+// FP32 (cpab_f32x2.cuh).  Loads/stores of the planar [ndim,nP] point arrays are unit-stride per
 // coordinate.  The loop trip count is fixed (nstepsolver), so divergence is confined to the rare
-// exact paths of the cell search.
+// exact paths of the cell search and to the flushes of the per-thread gradient accumulators.
 #include <atomic>
 #include <string_view>
 #include <type_traits>
