@@ -33,7 +33,7 @@ int g_interp_variant = 2;   // 0: 4 points in flight, 1 CTA/SM target; 1: 2 / 6;
 // host checks that one sample's grid, input and output each have < 2^31 elements); a thread owns
 // 4 points and issues all their gathers for a channel before blending.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NDIM, bool FULL, int BATCH>
+template <typename T, int NDIM, bool FULL, int BATCH, bool ONECH>
 __device__ __forceinline__ void interp_fwd_tile(const T* __restrict__ data, const T* __restrict__ grid,
                                                 T* __restrict__ out, const Shape& s,
                                                 T (&sg)[NDIM][TILE][TILE + 1])
@@ -71,7 +71,7 @@ __device__ __forceinline__ void interp_fwd_tile(const T* __restrict__ data, cons
     T* on = out + (size_t)n * s.C * nP + (NDIM == 2 ? (a0 + wrp) * s.O[1] + iF
                                                       : ((a0 + wrp) * s.O[1] + im) * s.O[2] + iF);
     const int ostride = 8 * (NDIM == 2 ? s.O[1] : s.O[1] * s.O[2]);     // output stride of one rep
-    const int nch = s.C;
+    const int nch = ONECH ? 1 : s.C;       // single-channel images: no channel loop at all
 #pragma unroll
     for (int r0 = 0; r0 < REPS; r0 += BATCH) {
         Taps<T, NDIM> tp[BATCH];
@@ -102,14 +102,14 @@ __device__ __forceinline__ void interp_fwd_tile(const T* __restrict__ data, cons
 
 // BATCH = points per thread whose gathers are in flight together; MINB = resident CTAs per SM
 // the register allocation targets (more CTAs hide the two dependent memory round trips per tile)
-template <typename T, int NDIM, int BATCH, int MINB>
+template <typename T, int NDIM, int BATCH, int MINB, bool ONECH = false>
 __global__ void __launch_bounds__(256, MINB)
 k_interp_fwd(const T* __restrict__ data, const T* __restrict__ grid, T* __restrict__ out, Shape s)
 {
     __shared__ T sg[NDIM][TILE][TILE + 1];
     const bool full = (blockIdx.x * TILE + TILE <= s.O[0]) && (blockIdx.y * TILE + TILE <= s.O[NDIM - 1]);
-    if (full) interp_fwd_tile<T, NDIM, true, BATCH>(data, grid, out, s, sg);
-    else interp_fwd_tile<T, NDIM, false, BATCH>(data, grid, out, s, sg);
+    if (full) interp_fwd_tile<T, NDIM, true, BATCH, ONECH>(data, grid, out, s, sg);
+    else interp_fwd_tile<T, NDIM, false, BATCH, ONECH>(data, grid, out, s, sg);
 }
 
 // 1-D: no transposition needed.  A thread owns PT points (strided by the CTA width so that every
@@ -361,6 +361,7 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
             // keeps the plain configuration
             const int var = sizeof(T) == 4 ? g_interp_variant : 0;
             if (var == 1) k_interp_fwd<T, 2, 1, 6><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
+            else if (var == 2 && s.C == 1) k_interp_fwd<T, 2, 1, 8, true><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
             else if (var == 2) k_interp_fwd<T, 2, 1, 8><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
             else if (var == 3) k_interp_fwd<T, 2, 2, 5><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
             else if (var == 4) k_interp_fwd<T, 2, 2, 4><<<g, 256, 0, st>>>((const T*)data, (const T*)grid, (T*)out_or_dgrid, s);
