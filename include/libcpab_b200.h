@@ -50,6 +50,13 @@ extern "C" {
 /* flags */
 #define CPAB_FLAG_FAST_MATH 1   /* forward: contract a*b+c into FMAs (default: every operation
                                    rounded as the CPU reference does -> bit-identical results) */
+#define CPAB_FLAG_FAST_GRAD 2   /* backward: skip the cell-sequence certificate.  Default: every
+                                   trajectory provably follows the cells the reference's float32 RK2
+                                   iterates visit (libcpab/core/cpab_ops.cpp:289-366), so the gradient
+                                   differs from the reference's by rounding only; with this flag an
+                                   iterate within rounding of a cell face may follow the neighbouring
+                                   cell (~1e-6 per point and step; moves a theta's gradient by up to
+                                   ~1e-3 relative). */
 
 /* ABI revision of this header; bumped on any signature change. */
 int cpab_b200_abi_version(void);
@@ -126,8 +133,10 @@ int cpab_b200_backward_jacobian(int dtype, int ndim, const int* nc, int nsteps, 
                                 long nP, int broadcast, const void* points, const void* As,
                                 const void* Bs, void* jac, void* stream);
 
-/* Bytes of scratch cpab_b200_backward_theta needs: the per-cell gradient G [n_theta, D] followed by
- * the per-cell RK2 step records [n_theta, nC, 4|8|16].  The workspace must be 16-byte aligned. */
+/* Bytes of scratch cpab_b200_backward_theta needs: the per-cell gradient G [n_theta, D], the
+ * per-cell RK2 step records [n_theta, nC, 2|8|16], the per-theta certificate bounds and the work
+ * counter of the launch.  The workspace must be 16-byte aligned; it is written by the call only
+ * (no state survives it, concurrent calls need distinct workspaces). */
 size_t cpab_b200_backward_workspace_bytes(int dtype, int ndim, const int* nc, int n_theta);
 
 /*
@@ -138,12 +147,34 @@ size_t cpab_b200_backward_workspace_bytes(int dtype, int ndim, const int* nc, in
  *   basis    [D, d] (row-major, as params.basis)
  *   grad_out [n_theta, ndim, nP]    dtheta   [n_theta, d]  out
  *   dpoints  [n_theta, ndim, nP]    out, may be NULL (the reference returns None for it)
+ *   flags    0 (certified cell sequences, see CPAB_FLAG_FAST_GRAD) or CPAB_FLAG_FAST_GRAD
  */
 int cpab_b200_backward_theta(int dtype, int flags, int ndim, const int* nc, int nsteps,
                              int n_theta, int d, long nP, int broadcast, const void* points,
                              const void* As, const void* basis, const void* grad_out,
                              void* dtheta, void* dpoints, void* workspace, size_t workspace_bytes,
                              void* stream);
+
+/* As cpab_b200_backward_theta, plus diagnostics: redo_count [n_theta] int32 (zeroed by the caller)
+ * receives the number of trajectories per theta whose certificate failed and which were
+ * re-integrated with the reference's arithmetic.  May be NULL. */
+int cpab_b200_backward_theta_diag(int dtype, int flags, int ndim, const int* nc, int nsteps,
+                                  int n_theta, int d, long nP, int broadcast, const void* points,
+                                  const void* As, const void* basis, const void* grad_out,
+                                  void* dtheta, void* dpoints, void* workspace, size_t workspace_bytes,
+                                  int* redo_count, void* stream);
+
+/*
+ * Test / diagnostic door: the cell index the adjoint's first pass records at every RK2 step
+ * (float32).  mode 0: step records + complete search (what CPAB_FLAG_FAST_GRAD integrates),
+ * mode 1: step records + certified fast search (failed[t,i] = 1 where the certificate fails),
+ * mode 2: the reference's arithmetic (libcpab/core/cpab_ops.cpp:289-366, p-recursion only).
+ *   cells  [n_theta, nsteps, nP] int32 out     failed [n_theta, nP] uint8 out, may be NULL
+ *   workspace as for cpab_b200_backward_theta (CPAB_F32).
+ */
+int cpab_b200_rk2_cell_trace(int ndim, const int* nc, int nsteps, int n_theta, long nP, int broadcast,
+                             int mode, const void* points, const void* As, void* workspace,
+                             size_t workspace_bytes, int* cells, unsigned char* failed, void* stream);
 
 /*
  * Closed-form ("hit-time") integration, 1-D only; OPT-IN extension, no counterpart in the
@@ -195,9 +226,9 @@ int cpab_b200_transform_data_forward(int dtype, int flags, int ndim, const int* 
                                      const void* points, const void* trels, const void* data,
                                      void* grid_t, void* out, void* stream);
 
-/* dL/dtheta of the above from grad_out [n_theta, C, out_size...]; workspace as for
+/* dL/dtheta of the above from grad_out [n_theta, C, out_size...]; workspace and flags as for
  * cpab_b200_backward_theta.  (dL/ddata, if wanted, is cpab_b200_interpolate_backward's.) */
-int cpab_b200_transform_data_backward(int dtype, int ndim, const int* nc, int nsteps, int n_theta,
+int cpab_b200_transform_data_backward(int dtype, int flags, int ndim, const int* nc, int nsteps, int n_theta,
                                       int d, int C, const int* in_size, const int* out_size,
                                       const void* points, const void* As, const void* basis,
                                       const void* data, const void* grid_t, const void* grad_out,

@@ -17,7 +17,8 @@ _lib = None
 
 CPAB_F32, CPAB_F64 = 0, 1
 CPAB_FLAG_FAST_MATH = 1
-ABI_VERSION = 1
+CPAB_FLAG_FAST_GRAD = 2
+ABI_VERSION = 2
 
 _vp, _i, _l, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_size_t
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -40,12 +41,15 @@ SIGNATURES = {
     "cpab_b200_backward_workspace_bytes": (_sz, [_i, _i, _ip, _i]),
     "cpab_b200_backward_theta": (_i, [_i, _i, _i, _ip, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _sz, _vp]),
+    "cpab_b200_backward_theta_diag": (_i, [_i, _i, _i, _ip, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _sz, _vp, _vp]),
+    "cpab_b200_rk2_cell_trace": (_i, [_i, _ip, _i, _i, _l, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "cpab_b200_forward_closed_form": (_i, [_i, _i, _ip, _i, _l, _i, _vp, _vp, _vp, _vp]),
     "cpab_b200_backward_theta_closed_form": (_i, [_i, _i, _ip, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp,
                                                   _vp, _vp, _sz, _vp]),
     "cpab_b200_interpolate_forward": (_i, [_i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp]),
     "cpab_b200_transform_data_forward": (_i, [_i, _i, _i, _ip, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "cpab_b200_transform_data_backward": (_i, [_i, _i, _ip, _i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp,
+    "cpab_b200_transform_data_backward": (_i, [_i, _i, _i, _ip, _i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp,
                                                _vp, _vp, _vp, _sz, _vp]),
     "cpab_b200_interpolate_backward": (_i, [_i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp,
                                             _vp]),
@@ -69,7 +73,7 @@ def load() -> ctypes.CDLL:
         path = os.environ.get("LIBCPAB_B200_SO")      # development: an experimental build of the same ABI
         if not path:
             path = _build.LIB
-            if not os.path.exists(path):
+            if _build.needs_build():
                 _build.build()      # raises if nvcc is missing: no silent fallback
         lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():

@@ -14,8 +14,10 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SOURCES = ["cpab_abi.cu", "cpab_integrate.cu", "cpab_expm.cu", "cpab_interp.cu", "cpab_probe.cu", "cpab_closed1d.cu"]
-HEADERS = ["cpab_common.cuh", "cpab_cell.cuh", os.path.join("..", "..", "include", "libcpab_b200.h")]
+SOURCES = ["cpab_abi.cu", "cpab_integrate.cu", "cpab_adjoint_1d.cu", "cpab_adjoint_2d.cu", "cpab_adjoint_3d.cu",
+           "cpab_expm.cu", "cpab_interp.cu", "cpab_probe.cu", "cpab_closed1d.cu"]
+HEADERS = ["cpab_common.cuh", "cpab_cell.cuh", "cpab_f32x2.cuh", "cpab_sample.cuh", "cpab_device.cuh", "cpab_adjoint.cuh",
+           os.path.join("..", "..", "include", "libcpab_b200.h")]
 LIB = os.path.join(CSRC, "libcpab_b200.so")
 
 NVCC_FLAGS = [
@@ -34,11 +36,26 @@ def _nvcc() -> str:
     return nvcc
 
 
+STAMP = LIB + ".srchash"
+
+
+def _source_hash() -> str:
+    """Content hash of every source and header (mtimes do not survive a repository snapshot)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    """True when the library is absent or was built from different sources."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    with open(STAMP) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -67,6 +84,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    with open(STAMP, "w") as f:
+        f.write(_source_hash())
     return LIB
 
 

@@ -100,13 +100,13 @@ using namespace cpab;
 
 extern "C" {
 
-int cpab_b200_abi_version(void) { return 1; }
+int cpab_b200_abi_version(void) { return 2; }
 
 const char* cpab_b200_last_error(void) { return get_error(); }
 
 const char* cpab_b200_build_info(void)
 {
-    return "libcpab_b200;arch=sm_100a;cuda=" CPAB_STR(CUDART_VERSION) ";abi=1";
+    return "libcpab_b200;arch=sm_100a;cuda=" CPAB_STR(CUDART_VERSION) ";abi=2";
 }
 
 int cpab_b200_set_tuning(const char* key, int value)
@@ -215,7 +215,38 @@ int cpab_b200_backward_theta(int dtype, int flags, int ndim, const int* nc, int 
     REQUIRE(n_theta == 0 || nP == 0 || (points && grad_out), "NULL pointer argument");
     return launch_backward(dtype, flags, make_geom(ndim, nc), nsteps, n_theta, d, nP, broadcast,
                            points, As, basis, grad_out, dtheta, dpoints, workspace,
-                           workspace_bytes, (cudaStream_t)stream);
+                           workspace_bytes, nullptr, (cudaStream_t)stream);
+}
+
+int cpab_b200_backward_theta_diag(int dtype, int flags, int ndim, const int* nc, int nsteps,
+                                  int n_theta, int d, long nP, int broadcast, const void* points,
+                                  const void* As, const void* basis, const void* grad_out,
+                                  void* dtheta, void* dpoints, void* workspace, size_t workspace_bytes,
+                                  int* redo_count, void* stream)
+{
+    if (!check_geom(dtype, ndim, nc)) return kErrArgument;
+    REQUIRE(nsteps > 0, "nstepsolver = %d must be positive", nsteps);
+    REQUIRE(n_theta >= 0 && nP >= 0 && d >= 0, "negative size");
+    REQUIRE(broadcast == 0 || broadcast == 1, "broadcast must be 0 or 1");
+    REQUIRE(n_theta == 0 || d == 0 || (As && basis && dtheta && workspace), "NULL pointer argument");
+    REQUIRE(n_theta == 0 || nP == 0 || (points && grad_out), "NULL pointer argument");
+    return launch_backward(dtype, flags, make_geom(ndim, nc), nsteps, n_theta, d, nP, broadcast,
+                           points, As, basis, grad_out, dtheta, dpoints, workspace,
+                           workspace_bytes, redo_count, (cudaStream_t)stream);
+}
+
+int cpab_b200_rk2_cell_trace(int ndim, const int* nc, int nsteps, int n_theta, long nP, int broadcast,
+                             int mode, const void* points, const void* As, void* workspace,
+                             size_t workspace_bytes, int* cells, unsigned char* failed, void* stream)
+{
+    if (!check_geom(kF32, ndim, nc)) return kErrArgument;
+    REQUIRE(nsteps > 0, "nstepsolver = %d must be positive", nsteps);
+    REQUIRE(n_theta >= 0 && nP >= 0, "negative size");
+    REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    REQUIRE(broadcast == 0 || broadcast == 1, "broadcast must be 0 or 1");
+    REQUIRE(n_theta == 0 || nP == 0 || (points && As && workspace && cells), "NULL pointer argument");
+    return launch_rk2_trace(make_geom(ndim, nc), nsteps, n_theta, nP, broadcast, mode, points, As,
+                            workspace, workspace_bytes, cells, failed, (cudaStream_t)stream);
 }
 
 int cpab_b200_forward_closed_form(int dtype, int ndim, const int* nc, int n_theta, long nP,
@@ -299,7 +330,7 @@ int cpab_b200_transform_data_forward(int dtype, int flags, int ndim, const int* 
                                          out_size, points, trels, data, grid_t, out, (cudaStream_t)stream);
 }
 
-int cpab_b200_transform_data_backward(int dtype, int ndim, const int* nc, int nsteps, int n_theta,
+int cpab_b200_transform_data_backward(int dtype, int flags, int ndim, const int* nc, int nsteps, int n_theta,
                                       int d, int C, const int* in_size, const int* out_size,
                                       const void* points, const void* As, const void* basis,
                                       const void* data, const void* grid_t, const void* grad_out,
@@ -313,7 +344,7 @@ int cpab_b200_transform_data_backward(int dtype, int ndim, const int* nc, int ns
     REQUIRE(d >= 0, "negative size");
     REQUIRE(n_theta == 0 || d == 0 || (points && As && basis && data && grid_t && grad_out && dtheta && workspace),
             "NULL pointer argument");
-    return launch_transform_data_backward(dtype, make_geom(ndim, nc), nsteps, n_theta, d, C, in_size,
+    return launch_transform_data_backward(dtype, flags, make_geom(ndim, nc), nsteps, n_theta, d, C, in_size,
                                           out_size, points, As, basis, data, grid_t, grad_out, dtheta,
                                           workspace, workspace_bytes, (cudaStream_t)stream);
 }

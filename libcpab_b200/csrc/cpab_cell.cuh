@@ -396,11 +396,12 @@ CPAB_HD_NOINLINE int find_cell_3d_replay(T q0, T q1, T q2, const Geom& g)
 // Fast path; returns true when the point lies within the guard band of a separating plane and
 // needs the exact replay (`cell` is then not meaningful).  The outside-the-box push stays inline:
 // zero-boundary flows park points on the faces, where they wobble an ulp outside on many steps.
-CPAB_HD bool find_cell_3d_fast(float p0, float p1, float p2, const Geom& g, int& cell, float* q)
+template <bool NEAR>
+CPAB_HD bool find_cell_3d_fast_t(float p0, float p1, float p2, const Geom& g, int& cell, float* q, float& dist)
 {
     float q0 = p0, q1 = p1, q2 = p2;
-    if (q0 < 0.0f || q0 > 1.0f || q1 < 0.0f || q1 > 1.0f)       // sic: z is not tested (:119)
-        push_inside_3d<float>(q0, q1, q2, g.w[0], g.w[1], g.w[2]);
+    const bool outside = q0 < 0.0f || q0 > 1.0f || q1 < 0.0f || q1 > 1.0f;   // sic: z is not tested (:119)
+    if (outside) push_inside_3d<float>(q0, q1, q2, g.w[0], g.w[1], g.w[2]);
     q[0] = q0; q[1] = q1; q[2] = q2;
     float kx, ky, kz, rx, ry, rz;
     const float c0 = fminf(g.hi3[0], fmaxf(0.0f, q0)), c1 = fminf(g.hi3[1], fmaxf(0.0f, q1));
@@ -432,7 +433,17 @@ CPAB_HD bool find_cell_3d_fast(float p0, float p1, float p2, const Geom& g, int&
     const float nearest = fminf(fminf(fabsf(t1), fabsf(t2)), fminf(fabsf(t3), fabsf(t4)));
     const int tet = (t1 >= 0.0f) ? 1 : (t2 >= 0.0f) ? 2 : (t3 >= 0.0f) ? 3 : (t4 >= 0.0f) ? 4 : 0;
     cell = 5 * cube + tet;
+    if (NEAR) {     // distance (local units) from the nearest face of the tetrahedron, cube faces included
+        const float lo3 = fminf(fminf(x, y), z), hi3 = fmaxf(fmaxf(x, y), z);
+        dist = fminf(nearest, fminf(lo3, 1.0f - hi3));
+        if (outside) dist = -1.0f;      // the push is discontinuous in the point: never certified
+    }
     return nearest < 4e-6f;
+}
+CPAB_HD bool find_cell_3d_fast(float p0, float p1, float p2, const Geom& g, int& cell, float* q)
+{
+    float dist;
+    return find_cell_3d_fast_t<false>(p0, p1, p2, g, cell, q, dist);
 }
 
 CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g)
@@ -450,6 +461,94 @@ CPAB_HD int find_cell_3d(double p0, double p1, double p2, const Geom& g)
         push_inside_3d<double>(q0, q1, q2, g.wd[0], g.wd[1], g.wd[2]);
     return find_cell_3d_replay<double>(q0, q1, q2, g);
 }
+
+// ------------------------------------------------------------------ certified search (float32)
+// find_cell_near: the fast-path cell of a point together with `dist`, a lower bound -- in local
+// cell units (fractions of a cell width) -- of the distance of the point from the nearest face of
+// its simplex, domain boundary included.  The strict adjoint uses it as a certificate: a fast RK2
+// iterate that is further than the accumulated rounding bound from every face lies in the same
+// simplex as the reference's iterate, so the recorded cell sequence is the reference's
+// (cpab_integrate.cu, "cell-sequence certificate").  No exact path here: whenever the fast search
+// would need one (point within the guard band of a diagonal, column estimate one too large,
+// coordinate clamped or pushed from outside the domain) `dist` is below every margin the
+// certificate uses (>= band2 in 2-D, 4e-6 in 3-D), and the caller re-integrates that trajectory
+// with the complete search instead.  A moved perturbation of |dp| (max norm, absolute) changes
+// `dist` by at most |dp| * cert_scale(g).
+CPAB_HD int find_cell_1d_near(float p0, const Geom& g, float magic, float& dist)
+{
+    // t = p * n is the reference's own rounded product (cpab_ops.cpp:28); rint and floor of it
+    // come from one magic add (|t| < 2^22; beyond, `dist` is 0 or NaN-free garbage >= 0 and the
+    // integer clamp below keeps the index in range)
+    const float t = p0 * g.nf[0];
+    const float tk = t + magic;
+    const float kf = tk - magic;                             // rint(t)
+    const float diff = t - kf;
+    dist = fabsf(diff);
+#if defined(__CUDA_ARCH__)
+    int c = (__float_as_int(tk) - __float_as_int(magic)) + (__float_as_int(diff) >> 31);   // floor(t) when diff != 0
+    return min(max(c, 0), g.nc[0] - 1);
+#else
+    const float c = fminf(fmaxf(floorf(t), 0.0f), g.nf[0] - 1.0f);
+    return (int)c;
+#endif
+}
+
+CPAB_HD int find_cell_2d_near(float p0, float p1, const Geom& g, float magic, float& dist)
+{
+    const float c0 = fminf(fmaxf(p0, 0.0f), g.hi2[0]), c1 = fminf(fmaxf(p1, 0.0f), g.hi2[1]);
+    float kx, ky, xf, yf, u, v, d1, d2;
+#if defined(__CUDA_ARCH__)
+    const F2 pc = pk(c0, c1), mg = bc(magic);
+    const F2 kf = sub2(fma2_rm(pc, pk(g.nup[0], g.nup[1]), mg), mg);
+    const F2 r = fma2(kf, pk(-g.w[0], -g.w[1]), pc);
+    const F2 xy = mul2(r, pk(g.nf[0], g.nf[1]));             // local coordinates (negative: estimate one too large)
+    const F2 uv = sub2(bc(1.0f), xy);
+    unpk(kf, kx, ky);
+    unpk(xy, xf, yf);
+    unpk(uv, u, v);
+    const F2 dd = sub2(pk(xf, u), bc(yf));                   // (x - y, 1 - x - y)
+    unpk(dd, d1, d2);
+    const int tri = ((__float_as_int(d1) >> 31) & 3) ^ (int)((unsigned)__float_as_int(d2) >> 31);
+#else
+    float rx, ry;
+    divmod_up(c0, g.nup[0], g.w[0], magic, kx, rx);
+    divmod_up(c1, g.nup[1], g.w[1], magic, ky, ry);
+    xf = rx * g.nf[0]; yf = ry * g.nf[1];
+    u = 1.0f - xf; v = 1.0f - yf;
+    d1 = xf - yf; d2 = u - yf;
+    const int tri = (d1 < 0.0f ? 3 : 0) ^ (d2 < 0.0f ? 1 : 0);
+#endif
+    dist = fminf(fminf(fminf(xf, yf), fminf(u, v)), fminf(fabsf(d1), fabsf(d2)));
+    return 4 * (int)fmaf(ky, g.nf[0], kx) + tri;
+}
+
+// bound of d(dist)/d|p|_inf: axis faces move by n_j, the diagonal planes by the sum over the axes
+CPAB_HD float cert_scale(const Geom& g)
+{
+    float s = 0.0f;
+    for (int j = 0; j < g.ndim; ++j) s += g.nf[j];
+    return s;
+}
+// floor of every certificate margin: the guard band of the fast search itself
+CPAB_HD float cert_floor(const Geom& g)
+{
+    return g.ndim == 1 ? 4.0f * 5.9604645e-08f * g.nf[0] : g.ndim == 2 ? g.band2 : 4e-6f;
+}
+
+CPAB_HD int find_cell_3d_near(float p0, float p1, float p2, const Geom& g, float& dist)
+{
+    int cell;
+    float q[3];
+    find_cell_3d_fast_t<true>(p0, p1, p2, g, cell, q, dist);
+    return cell;
+}
+template <int NDIM> CPAB_HD int find_cell_near(const float* p, const Geom& g, float magic, float& dist)
+{
+    if (NDIM == 1) return find_cell_1d_near(p[0], g, magic, dist);
+    if (NDIM == 2) return find_cell_2d_near(p[0], p[1], g, magic, dist);
+    return find_cell_3d_near(p[0], p[1], p[2], g, dist);
+}
+template <int NDIM> CPAB_HD int find_cell_near(const double* p, const Geom& g, float, float& dist);   // float32 only
 
 // ------------------------------------------------------------------------------- generic front end
 template <int NDIM, typename T>

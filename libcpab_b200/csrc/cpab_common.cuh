@@ -22,6 +22,8 @@ enum DType : int { kF32 = 0, kF64 = 1 };
 
 enum Flags : int {
     kFlagFastMath = 1,      // forward: allow FMA contraction (not bit-exact with the CPU reference)
+    kFlagFastGrad = 2,      // backward: skip the cell-sequence certificate (cpab_adjoint.cuh); a trajectory
+                            // that lands within rounding of a cell face may then follow a neighbouring cell
 };
 
 #define CPAB_STR2(x) #x
@@ -72,12 +74,15 @@ size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta);   // G +
 int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int d, long nP,
                     int broadcast, const void* points, const void* As, const void* basis,
                     const void* grad_out, void* dtheta, void* dpoints, void* workspace,
-                    size_t workspace_bytes, cudaStream_t st);
+                    size_t workspace_bytes, int* flagged, cudaStream_t st);
+int launch_rk2_trace(const Geom& g, int nsteps, int n_theta, long nP, int broadcast, int mode,
+                     const void* points, const void* As, void* workspace, size_t workspace_bytes,
+                     int* cells, unsigned char* failed, cudaStream_t st);
 int launch_transform_data_forward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int C,
                                   const int* in_size, const int* out_size, const void* points,
                                   const void* trels, const void* data, void* grid_t, void* img,
                                   cudaStream_t st);
-int launch_transform_data_backward(int dtype, const Geom& g, int nsteps, int n_theta, int d, int C,
+int launch_transform_data_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int d, int C,
                                    const int* in_size, const int* out_size, const void* points,
                                    const void* As, const void* basis, const void* data,
                                    const void* grid_t, const void* gimg, void* dtheta, void* workspace,

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CPAB_F32, CPAB_F64, CPAB_FLAG_FAST_MATH, check, nc_array
+from ._lib import CPAB_F32, CPAB_F64, CPAB_FLAG_FAST_GRAD, CPAB_FLAG_FAST_MATH, check, nc_array
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -131,8 +131,13 @@ def backward_jacobian(points: torch.Tensor, As: torch.Tensor, Bs: torch.Tensor, 
 
 
 def backward_theta(points: torch.Tensor, As: torch.Tensor, basis: torch.Tensor,
-                   grad_out: torch.Tensor, nc, nsteps: int, want_dpoints: bool = False):
-    """Adjoint gradient: dL/dtheta [n_theta,d] (and dL/dpoints [n_theta,ndim,nP] on request)."""
+                   grad_out: torch.Tensor, nc, nsteps: int, want_dpoints: bool = False,
+                   fast_grad: bool = False, redo_count: torch.Tensor = None):
+    """Adjoint gradient: dL/dtheta [n_theta,d] (and dL/dpoints [n_theta,ndim,nP] on request).
+
+    Default: every trajectory follows the cell sequence of the reference's float32 RK2 iterates
+    (certified, or re-integrated with the reference's arithmetic); `fast_grad=True` skips that.
+    `redo_count` (int32 [n_theta], zeroed) receives the number of re-integrated trajectories."""
     points, As = _req(points, "points"), _req(As, "As")
     basis, grad_out = _req(basis, "basis"), _req(grad_out, "grad_out")
     n_theta = As.shape[0]
@@ -148,13 +153,36 @@ def backward_theta(points: torch.Tensor, As: torch.Tensor, basis: torch.Tensor,
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=points.device)
     dtheta = torch.empty((n_theta, d), dtype=points.dtype, device=points.device)
     dpoints = torch.empty_like(grad_out) if want_dpoints else None
+    flags = CPAB_FLAG_FAST_GRAD if fast_grad else 0
     with torch.cuda.device(points.device):
-        check(lib.cpab_b200_backward_theta(code, 0, ndim, nc_array(nc), int(nsteps), n_theta, d, nP,
-                                           broadcast, points.data_ptr(), As.data_ptr(),
-                                           basis.data_ptr(), grad_out.data_ptr(), dtheta.data_ptr(),
-                                           dpoints.data_ptr() if want_dpoints else None,
-                                           ws.data_ptr(), ws_bytes, _stream()), "backward_theta")
+        check(lib.cpab_b200_backward_theta_diag(code, flags, ndim, nc_array(nc), int(nsteps), n_theta, d, nP,
+                                                broadcast, points.data_ptr(), As.data_ptr(),
+                                                basis.data_ptr(), grad_out.data_ptr(), dtheta.data_ptr(),
+                                                dpoints.data_ptr() if want_dpoints else None,
+                                                ws.data_ptr(), ws_bytes,
+                                                redo_count.data_ptr() if redo_count is not None else None,
+                                                _stream()), "backward_theta")
     return dtheta, dpoints
+
+
+def rk2_cell_trace(points: torch.Tensor, As: torch.Tensor, nc, nsteps: int, mode: int):
+    """Cells recorded by the adjoint's first pass (tests / diagnostics): (cells int32
+    [n_theta,nsteps,nP], failed uint8 [n_theta,nP]); mode 0 records, 1 certified, 2 reference."""
+    points, As = _req(points, "points"), _req(As, "As")
+    if points.dtype != torch.float32:
+        raise TypeError("rk2_cell_trace is a float32 diagnostic")
+    n_theta = As.shape[0]
+    broadcast, ndim, nP = _points_layout(points, n_theta)
+    lib = _lib.load()
+    ws_bytes = lib.cpab_b200_backward_workspace_bytes(CPAB_F32, ndim, nc_array(nc), n_theta)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=points.device)
+    cells = torch.empty((n_theta, int(nsteps), nP), dtype=torch.int32, device=points.device)
+    failed = torch.zeros((n_theta, nP), dtype=torch.uint8, device=points.device)
+    with torch.cuda.device(points.device):
+        check(lib.cpab_b200_rk2_cell_trace(ndim, nc_array(nc), int(nsteps), n_theta, nP, broadcast, int(mode),
+                                           points.data_ptr(), As.data_ptr(), ws.data_ptr(), ws_bytes,
+                                           cells.data_ptr(), failed.data_ptr(), _stream()), "rk2_cell_trace")
+    return cells, failed
 
 
 def forward_closed_form(points: torch.Tensor, As: torch.Tensor, nc) -> torch.Tensor:
@@ -263,7 +291,7 @@ def transform_data_forward(points: torch.Tensor, trels: torch.Tensor, data: torc
     return out, grid_t
 
 
-def transform_data_backward(points, As, basis, data, grid_t, grad_out, nc, nsteps: int):
+def transform_data_backward(points, As, basis, data, grid_t, grad_out, nc, nsteps: int, fast_grad: bool = False):
     """dL/dtheta of the fused transform_data from the image gradient grad_out [n_theta,C,*outsize]."""
     points, As, basis = _req(points, "points"), _req(As, "As"), _req(basis, "basis")
     data, grid_t, grad_out = _req(data, "data"), _req(grid_t, "grid_t"), _req(grad_out, "grad_out")
@@ -277,7 +305,8 @@ def transform_data_backward(points, As, basis, data, grid_t, grad_out, nc, nstep
     dtheta = torch.empty((n_theta, d), dtype=data.dtype, device=data.device)
     with torch.cuda.device(data.device):
         check(lib.cpab_b200_transform_data_backward(
-            code, ndim, nc_array(nc), int(nsteps), n_theta, d, C, ctypes_int_array(data.shape[2:]),
+            code, CPAB_FLAG_FAST_GRAD if fast_grad else 0, ndim, nc_array(nc), int(nsteps), n_theta, d, C,
+            ctypes_int_array(data.shape[2:]),
             ctypes_int_array(grad_out.shape[2:]), points.data_ptr(), As.data_ptr(), basis.data_ptr(),
             data.data_ptr(), grid_t.data_ptr(), grad_out.data_ptr(), dtheta.data_ptr(), ws.data_ptr(),
             ws_bytes, _stream()), "transform_data_backward")

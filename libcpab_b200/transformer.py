@@ -71,7 +71,8 @@ class _CpabFunction(torch.autograd.Function):
                                                              want_dpoints=ctx.points_need_grad)
         else:
             dtheta, dpoints = ops.backward_theta(points, As, B, grad.contiguous(), p.nc, p.nstepsolver,
-                                                 want_dpoints=ctx.points_need_grad)
+                                                 want_dpoints=ctx.points_need_grad,
+                                                 fast_grad=bool(getattr(p, "fast_grad", False)))
         if dpoints is not None and points.dim() == 2:
             dpoints = dpoints.sum(dim=0)          # one grid shared by every theta
         return dpoints, dtheta, None
@@ -100,7 +101,8 @@ class _TransformDataFunction(torch.autograd.Function):
         grad = grad.contiguous()
         dtheta = ddata = None
         if ctx.needs_input_grad[1]:
-            dtheta = ops.transform_data_backward(grid, As, B, data, grid_t, grad, p.nc, p.nstepsolver)
+            dtheta = ops.transform_data_backward(grid, As, B, data, grid_t, grad, p.nc, p.nstepsolver,
+                                                 fast_grad=bool(getattr(p, "fast_grad", False)))
         if ctx.needs_input_grad[0]:
             _, ddata = ops.interpolate_backward(data, grid_t, grad, want_dgrid=False, want_ddata=True)
         return ddata, dtheta, None, None, None

@@ -210,6 +210,22 @@ def rk2_flow(points: np.ndarray, As: np.ndarray, nc, nsteps: int = 50) -> np.nda
     return out
 
 
+def rk2_trace(points: np.ndarray, As: np.ndarray, nc, nsteps: int = 50):
+    """(cells int32 [n_theta,nsteps,nP], end points) of the RK2 trajectories; cpab_ops.cpp:289-366."""
+    As = np.ascontiguousarray(As)
+    points = np.ascontiguousarray(points, dtype=As.dtype)
+    n_theta = As.shape[0]
+    broadcast = int(points.ndim == 3 and points.shape[0] == n_theta)
+    ndim = points.shape[1] if broadcast else points.shape[0]
+    nP = points.shape[-1]
+    out = np.empty((n_theta, ndim, nP), dtype=As.dtype)
+    cells = np.empty((n_theta, nsteps, nP), dtype=np.int32)
+    fn = getattr(oracle_lib(), "cpab_oracle_rk2_trace_" + _suffix(As.dtype))
+    fn(_ptr(cells), _ptr(out), _ptr(points), _ptr(As), ctypes.c_int(nsteps), _ptr(_nc_arr(nc)),
+       ctypes.c_int(n_theta), ctypes.c_int(ndim), ctypes.c_long(nP), ctypes.c_int(broadcast))
+    return cells, out
+
+
 def _split(run, n, threads):
     """Run ``run(lo,hi)`` over [0,n) in ``threads`` chunks (ctypes releases the GIL)."""
     threads = max(1, min(int(threads), n))

@@ -74,21 +74,31 @@ def theta_errs(got, ref):
     return np.abs(got - ref).reshape(len(ref), -1).max(axis=1) / den
 
 
-def assert_grad_parity(got, ref, tol=1e-5, flip_bound=2e-3):
-    """float32 theta-gradient against the reference's float32 gradient.
+def assert_grad_parity(got, ref, tol=1e-5, what=""):
+    """float32 theta-gradient against the reference's float32 gradient: EVERY theta within `tol`
+    (north_star: 1e-5 relative, relative = max|x-ref| / max|ref|).
 
-    The discretised flow is piecewise affine in the point, so its Jacobian jumps across cell faces.
-    An RK2 iterate that lands within an ulp of a face is assigned to one or the other cell by any
-    implementation that does not reproduce every rounding of the reference's CPU build (its own
-    CUDA build, FMA-contracted by nvcc, does not either).  Such a "flip" happens about once per
-    1e6 (point, step) events and moves that theta's gradient by ~ h |A_c - A_c'| / nP ~ 1e-5..1e-4
-    relative -- the reference's float32 and float64 gradients differ by 5e-4 on BASELINE
-    configs[0] for the same reason (tests/test_oracle_pinned.py).  The float64 check mode, where
-    flips have probability ~1e-15, is held to 1e-10 with no exception.  Here: the bulk of the
-    thetas within `tol`, at most max(1, 10 %) flipped ones, and those within the flip bound.
+    The default backward follows, provably, the cell sequence of the reference's own float32 RK2
+    iterates (libcpab_b200/csrc/cpab_adjoint.cuh, "cell-sequence certificate"), so nothing but
+    rounding and summation order separates the two gradients.  Prints the achieved distribution
+    (`pytest -rP`).
+    """
+    errs = theta_errs(got, ref)
+    print("grad parity %s: thetas=%d max=%.3g median=%.3g above_tol=%d"
+          % (what, len(errs), errs.max(), float(np.median(errs)), int((errs >= tol).sum())))
+    assert errs.max() < tol, (what, np.sort(errs)[-5:])
+
+
+def assert_grad_parity_fast_mode(got, ref, tol=1e-5, flip_bound=2e-3, what=""):
+    """Bar of the opt-in CPAB_FLAG_FAST_GRAD mode, which skips the certificate: an RK2 iterate
+    within rounding of a cell face may then be assigned to the neighbouring cell ("flip", about
+    once per 1e6 (point, step) events; moves that theta's gradient by up to ~1e-3 relative).  The
+    bulk of the thetas within `tol`, at most max(1, 10 %) flipped ones, and those within the bound.
     """
     errs = theta_errs(got, ref)
     flipped = int((errs >= tol).sum())
+    print("grad parity (fast_grad) %s: thetas=%d max=%.3g median=%.3g above_tol=%d"
+          % (what, len(errs), errs.max(), float(np.median(errs)), flipped))
     assert flipped <= max(1, len(errs) // 10), (flipped, len(errs), np.sort(errs)[-5:])
     if len(errs) >= 4:
         assert np.median(errs) < tol, np.median(errs)
