@@ -133,11 +133,12 @@ int cpab_b200_backward_jacobian(int dtype, int ndim, const int* nc, int nsteps, 
                                 long nP, int broadcast, const void* points, const void* As,
                                 const void* Bs, void* jac, void* stream);
 
-/* Bytes of scratch cpab_b200_backward_theta needs: the per-cell gradient G [n_theta, D], the
- * per-cell RK2 step records [n_theta, nC, 2|8|16], the per-theta certificate bounds and the work
- * counter of the launch.  The workspace must be 16-byte aligned; it is written by the call only
- * (no state survives it, concurrent calls need distinct workspaces). */
-size_t cpab_b200_backward_workspace_bytes(int dtype, int ndim, const int* nc, int n_theta);
+/* Bytes of scratch cpab_b200_backward_theta needs for n_theta thetas x nP points: the per-cell
+ * gradient G [n_theta, D], the per-cell RK2 step records [n_theta, nC, 2|8|16], the per-theta
+ * certificate bounds, the work counters of the launch and (float32) one bit per trajectory for
+ * the certificate's verdict.  The workspace must be 16-byte aligned; it is written by the call
+ * only (no state survives it, concurrent calls need distinct workspaces). */
+size_t cpab_b200_backward_workspace_bytes(int dtype, int ndim, const int* nc, int n_theta, long nP);
 
 /*
  * dL/dtheta (and optionally dL/dpoints) in one adjoint sweep.  Replaces the pair

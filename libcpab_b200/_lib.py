@@ -38,7 +38,7 @@ SIGNATURES = {
     "cpab_b200_expm": (_i, [_i, _i, _l, _vp, _vp, _vp]),
     "cpab_b200_forward": (_i, [_i, _i, _i, _ip, _i, _i, _l, _i, _vp, _vp, _vp, _vp]),
     "cpab_b200_backward_jacobian": (_i, [_i, _i, _ip, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp]),
-    "cpab_b200_backward_workspace_bytes": (_sz, [_i, _i, _ip, _i]),
+    "cpab_b200_backward_workspace_bytes": (_sz, [_i, _i, _ip, _i, _l]),
     "cpab_b200_backward_theta": (_i, [_i, _i, _i, _ip, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _sz, _vp]),
     "cpab_b200_backward_theta_diag": (_i, [_i, _i, _i, _ip, _i, _i, _i, _l, _i, _vp, _vp, _vp, _vp,
@@ -102,7 +102,7 @@ def set_tuning(key: str, value: int) -> None:
 
 
 PROFILE_SLOTS = {"forward": 0, "backward": 1, "interp_fwd": 2, "interp_bwd": 3,
-                 "theta_to_trels": 4, "epilogue": 5}
+                 "theta_to_trels": 4, "epilogue": 5, "backward_redo": 6}
 
 
 def launch_count() -> int:

@@ -195,10 +195,10 @@ int cpab_b200_backward_jacobian(int dtype, int ndim, const int* nc, int nsteps, 
                            Bs, jac, (cudaStream_t)stream);
 }
 
-size_t cpab_b200_backward_workspace_bytes(int dtype, int ndim, const int* nc, int n_theta)
+size_t cpab_b200_backward_workspace_bytes(int dtype, int ndim, const int* nc, int n_theta, long nP)
 {
-    if (!check_geom(dtype, ndim, nc) || n_theta < 0) return 0;
-    return backward_workspace_bytes(dtype, make_geom(ndim, nc), n_theta);
+    if (!check_geom(dtype, ndim, nc) || n_theta < 0 || nP < 0) return 0;
+    return backward_workspace_bytes(dtype, make_geom(ndim, nc), n_theta, nP);
 }
 
 int cpab_b200_backward_theta(int dtype, int flags, int ndim, const int* nc, int nsteps,
@@ -281,7 +281,7 @@ int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int
     REQUIRE(n_theta == 0 || d == 0 || (As && basis && dtheta && workspace), "NULL pointer argument");
     REQUIRE(n_theta == 0 || nP == 0 || (points && grad_out), "NULL pointer argument");
     const Geom g = make_geom(ndim, nc);
-    const size_t need = backward_workspace_bytes(dtype, g, n_theta);
+    const size_t need = backward_workspace_bytes(dtype, g, n_theta, nP);
     if (workspace_bytes < need) { set_error("backward: workspace has %zu bytes, needs %zu", workspace_bytes, need); return kErrWorkspace; }
     if (n_theta == 0 || d == 0) return kOk;
     cudaStream_t st = (cudaStream_t)stream;

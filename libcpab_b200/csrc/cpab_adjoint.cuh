@@ -46,20 +46,24 @@
 // F2F.F64<->F32 conversions per 2-D step, and those run at 16 lanes/clk/SM on a B200
 // (profiles/r02_pipe_probe.txt) -- 80 SMSP-cycles per warp-step against ~95 for the whole sweep.
 // Instead, pass 1 integrates with the records and carries a certificate:
-//     Let f_n be the record iterate, r_n the reference iterate (f_0 = r_0).  While both have
-//     visited the same cells, |f_n - r_n|_inf <= n * eta * exp(a) =: m_n, where a bounds
-//     ||L_c||_inf over the cells of this theta, tau bounds |t_c|_inf, h = 1/nsteps, and
-//     eta = 2^-24 (2.5 + h (12 a + 8 tau)(1 + h a / 2)) bounds the per-step rounding of both
-//     schemes for iterates inside the unit box (derivation: DESIGN.md 2).
-//     find_cell_near() returns, with the fast-path cell of f_n, a lower bound `dist` of the
-//     distance of f_n from the nearest face of that simplex in local units; a perturbation of
-//     |dp|_inf moves it by at most |dp| * cert_scale.  If dist >= m_n * cert_scale + cert_floor
-//     at every step n >= 1 (step 0 uses the complete search on the bit-identical input), then by
-//     induction r_n lies in the same simplex as f_n at every step: the recorded cell sequence IS
-//     the reference's.
+//     Let f_n be the record iterate, r_n the reference iterate (f_0 = r_0), both inside the unit
+//     box.  While both have visited the same cells c_0..c_{n-1},
+//         |f_{n+1} - r_{n+1}|_inf <= ||I + D_c||_inf |f_n - r_n|_inf + eta,
+//     ||I + D_c||_inf = 1 + k_c,  k_c = max_i (D_ii + sum_{j != i} |D_ij|)   (|D_ii| < 1),
+//     eta = 2^-24 (1 + h (15 a + 9 tau)(1 + h a / 2)): half an ulp for each scheme's final
+//     rounding plus the rounding of the increments; a bounds ||L_c||_inf over the cells of this
+//     theta, tau bounds |t_c|_inf, h = 1/nsteps (derivation: DESIGN.md 2).  The kernel carries
+//     the bound along the trajectory with the record it has in registers anyway,
+//         M_{n+1} = (1 + k_{c_n}) M_n + eta * cert_scale,   M_0 = cert_floor,
+//     in the local units of find_cell_near(): that function returns, with the fast-path cell of
+//     f_n, a lower bound `dist` of the distance of f_n from the nearest face of that simplex;
+//     a perturbation of |dp|_inf moves it by at most |dp| * cert_scale, and cert_floor covers the
+//     search's own rounding.  If dist >= M_n at every step n >= 1 (step 0 uses the complete
+//     search on the bit-identical input), then by induction r_n lies in the same simplex as f_n
+//     at every step: the recorded cell sequence IS the reference's.
 // A trajectory that fails the test at some step (a few per cent: iterates that land next to a
-// face while crossing it, points parked on the domain boundary) is put on a per-unit list and
-// re-integrated by the same CTA with the reference's own arithmetic (float A p~ in the reference's
+// face while crossing it, points parked on the domain boundary) is marked in a bit mask and
+// re-integrated by a second kernel (k_backward_redo) with the reference's own arithmetic (float A p~ in the reference's
 // order, double-rounded updates, the complete cell search) -- bit-identical iterates, hence the
 // reference's cell sequence again.  Pass 2 is shared.  The gradient then differs from the
 // reference's only by summation order and record rounding, never by a different cell.
@@ -108,7 +112,8 @@ __device__ __forceinline__ void step_inc(const T* W, T* p)
 
 // One RK2 step with the reference's own arithmetic (cpab_ops.cpp:304-313,362-365): float A p~ in
 // the reference's order, `pMid = p + h*v/2.0` and `p += vMid*h` evaluated in double (h is a
-// double there) and rounded on store.  (h*v)/2.0 == (h/2)*v in binary arithmetic, overflow aside.
+// double there) and rounded on store.  (h*v)/2.0 == (h/2)*v bit for bit: halving is exact in binary
+// arithmetic (no underflow at these magnitudes), so it commutes with the rounding of the product.
 template <int NDIM>
 __device__ __forceinline__ void step_reference(const float* A, double h, float* p)
 {
@@ -116,7 +121,7 @@ __device__ __forceinline__ void step_reference(const float* A, double h, float* 
     affine_strict<NDIM>(A, p, v);
 #pragma unroll
     for (int j = 0; j < NDIM; ++j)
-        pm[j] = (float)__dadd_rn((double)p[j], __dmul_rn(__dmul_rn(h, (double)v[j]), 0.5));
+        pm[j] = (float)__dadd_rn((double)p[j], __dmul_rn(0.5 * h, (double)v[j]));
     affine_strict<NDIM>(A, pm, vm);
 #pragma unroll
     for (int j = 0; j < NDIM; ++j) p[j] = (float)__dadd_rn((double)p[j], __dmul_rn((double)vm[j], h));
@@ -127,7 +132,7 @@ __device__ __forceinline__ void step_reference(const double* A, double h, double
     double v[NDIM], pm[NDIM], vm[NDIM];
     affine_strict<NDIM>(A, p, v);
 #pragma unroll
-    for (int j = 0; j < NDIM; ++j) pm[j] = __dadd_rn(p[j], __dmul_rn(__dmul_rn(h, v[j]), 0.5));
+    for (int j = 0; j < NDIM; ++j) pm[j] = __dadd_rn(p[j], __dmul_rn(0.5 * h, v[j]));
     affine_strict<NDIM>(A, pm, vm);
 #pragma unroll
     for (int j = 0; j < NDIM; ++j) p[j] = __dadd_rn(p[j], __dmul_rn(vm[j], h));
@@ -181,36 +186,184 @@ __device__ __forceinline__ void flush_runs(T* __restrict__ Gg, int key, T* acc)
     if (tail && key >= 0) red_cell<PPC>(Gg + (size_t)key * PPC, acc);
 }
 
-// ---- work units drawn from a counter in the caller's workspace ------------------------------------
-// All threads of the CTA must call this; returns false when the work is exhausted.
-__device__ __forceinline__ bool next_unit(const WorkPlan& wp, long nP, unsigned* counter, unsigned* s_work, WorkUnit& u)
-{
-    __syncthreads();                                   // everyone is done with the previous unit
-    if (threadIdx.x == 0) *s_work = atomicAdd(counter, 1u);
-    __syncthreads();
-    const unsigned w = *s_work;
-    if (w >= wp.total) return false;
-    unit_of(wp, w, nP, u);
-    return true;
-}
-
 // Certificate inputs of one launch (float32 only).
 struct CertArgs {
     const void* As;        // [n_theta,nC,n,n+1] velocity fields, for the reference-arithmetic re-integration
     const float* stats;    // [n_theta][2]: max_c ||L_c||_inf and max_c |t_c|_inf (k_prepare_backward)
     float scale, floor;    // cert_scale(g), cert_floor(g)
+    unsigned* mask;        // [n_theta][words] one bit per trajectory: certificate failed, re-integrate
+    long words;            // 32-bit words per theta: ceil(nP / 32)
     int* flagged;          // optional [n_theta] counters of re-integrated trajectories (diagnostics), may be NULL
 };
 
-// per-step growth of the certificate margin, in the local units of find_cell_near (see the header)
-__device__ __forceinline__ float cert_slope(const CertArgs& ca, int theta, int nsteps)
+// eta * cert_scale of one theta: the per-step additive term of the certificate bound (see the header)
+__device__ __forceinline__ float cert_eta(const CertArgs& ca, int theta, int nsteps)
 {
     const float a = ca.stats[2 * theta], tau = ca.stats[2 * theta + 1];
     const float h = 1.0f / (float)nsteps;
-    const float eta = 5.9604645e-08f * (2.5f + h * (12.0f * a + 8.0f * tau) * (1.0f + 0.5f * h * a));
-    // (1.01: expf is not correctly rounded; a NaN/inf theta gives a NaN/inf slope and every
-    //  comparison `dist < m` is then false or true for all -- either way the result is NaN already)
-    return 1.01f * eta * expf(a) * ca.scale + ca.floor;
+    // |D_ii| < 1 is what makes ||I + D||_inf = 1 + k; a theta this wild (or NaN) certifies nothing
+    if (!(h * a < 0.5f)) return __int_as_float(0x7f800000);
+    // + 6e-8: k_c is evaluated from the rounded record (|error| < 1e-7) and multiplies a bound that is
+    // below 1/2 for every trajectory still certified (no point is further than that from a face)
+    return 1.001f * 5.9604645e-08f * (1.0f + h * (15.0f * a + 9.0f * tau) * (1.0f + 0.5f * h * a)) * ca.scale + 6e-8f;
+}
+// k_c of a step record held in registers: max_i (D_ii + sum_{j != i} |D_ij|), D column-major
+template <int NDIM>
+__device__ __forceinline__ float cert_gain(const float* W)
+{
+    if (NDIM == 1) return W[0];
+    if (NDIM == 2) return fmaxf(W[0] + fabsf(W[2]), W[3] + fabsf(W[1]));
+    return fmaxf(fmaxf(W[0] + (fabsf(W[3]) + fabsf(W[6])), W[4] + (fabsf(W[1]) + fabsf(W[7]))),
+                 W[8] + (fabsf(W[2]) + fabsf(W[5])));
+}
+template <int NDIM> __device__ __forceinline__ float cert_gain(const double*) { return 0.0f; }
+
+// =====================================================================================================
+// The two passes over one trajectory, shared by k_backward (all trajectories, step records) and
+// k_backward_redo (the trajectories whose certificate failed, reference arithmetic).
+// A thread owns one `slot` of the checkpoint / cell-trace arrays in shared memory (STRIDE slots).
+// =====================================================================================================
+template <typename T, int NDIM, int SEG>
+struct Sweep {
+    static constexpr int PPC = Dim<NDIM>::kPpc;
+    static constexpr int WS = StepRec<NDIM>::kStride;
+    T* ck;                 // checkpoints [nseg][NDIM][stride]
+    unsigned short* ct16;  // cell trace  [nsteps][stride]  (ct32 when `wide`)
+    int* ct32;
+    bool wide;
+    int stride, slot;
+    int nsteps, nseg;
+
+    // ---- pass 1: the RK2 trajectory from p.  Records the cell of every step and a checkpoint of p
+    //      at the start of every segment; the only pass that searches cells.
+    //      MODE 0: records + complete search (no certificate: float64, CPAB_FLAG_FAST_GRAD)
+    //      MODE 1: records + certified fast search; returns true (and stops early) when it fails
+    //      MODE 2: the reference's arithmetic + complete search
+    template <int MODE, typename Table>
+    __device__ __forceinline__ bool pass1(const Geom& g, const Table& table, const T* Ag, float m0, float eta_s,
+                                          float magic, T* p) const
+    {
+        bool failed = false;
+        float m = m0;                  // certificate bound M_n of the current step (local units)
+        int c_first = 0;
+        if (MODE == 1) c_first = find_cell<NDIM>(p, g);
+        auto segment = [&](int sg, auto full_tag) {     // FULL = a whole segment that is not the last one: no bounds checks
+            constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) ck[(sg * NDIM + j) * stride + slot] = p[j];
+#pragma unroll
+            for (int s = 0; s < SEG; ++s) {
+                const int n = sg * SEG + s;
+                if (FULL || n < nsteps) {
+                    int c;
+                    if constexpr (MODE == 1) {
+                        float dist;
+                        c = find_cell_near<NDIM>(p, g, magic, dist);
+                        if (s == 0 && sg == 0) { c = c_first; dist = 1.0f; }   // step 0: identical input, complete search
+                        failed |= dist < m;
+                    } else {
+                        c = find_cell<NDIM>(p, g);
+                    }
+                    if (wide) ct32[n * stride + slot] = c;
+                    else ct16[n * stride + slot] = (unsigned short)c;
+                    if (FULL || n + 1 < nsteps) {
+                        if constexpr (MODE == 2) {
+                            T a[PPC];
+                            load_affine<NDIM>(Ag + (size_t)c * PPC, a);
+                            step_reference<NDIM>(a, 1.0 / nsteps, p);
+                        } else {
+                            T w[WS];
+                            table.load(c, w);
+                            step_inc<NDIM>(w, p);
+                            if constexpr (MODE == 1) m = fmaf(m, cert_gain<NDIM>(w), m + eta_s);
+                        }
+                    }
+                }
+            }
+        };
+        int sg = 0;
+        for (; sg + 1 < nseg && !failed; ++sg) segment(sg, std::true_type{});
+        if (!failed) segment(nseg - 1, std::false_type{});
+        return failed;
+    }
+
+    // ---- pass 2: segments in reverse; replay p into registers (no search), sweep lambda back,
+    //      accumulate R_c += lambda_{n+1} [p_n;1]^T per thread and hand a cell's sum to R[theta]
+    //      (Gt) when the trajectory leaves the cell.  Leaves lambda_0 in lam.
+    template <typename Table>
+    __device__ __forceinline__ void pass2(const Table& table, T* Gt, T* lam, T* acc, int& cur) const
+    {
+        T p[NDIM];
+        auto segment = [&](int sg, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int len = FULL ? SEG : nsteps - sg * SEG;
+            T ps[SEG][NDIM];
+            T w[WS];
+            int cs[SEG];
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) p[j] = ck[(sg * NDIM + j) * stride + slot];
+#pragma unroll
+            for (int s = 0; s < SEG; ++s) {
+                if (FULL || s < len) {
+                    const int n = sg * SEG + s;
+                    cs[s] = wide ? ct32[n * stride + slot] : (int)ct16[n * stride + slot];
+#pragma unroll
+                    for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
+                    if (s + 1 < SEG && (FULL || s + 1 < len)) {
+                        table.load(cs[s], w);       // (the compiler keeps these for the sweep below)
+                        step_inc<NDIM>(w, p);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = SEG - 1; s >= 0; --s) {
+                if (FULL || s < len) {
+                    const int c = cs[s];
+                    table.load(c, w);
+                    if (c != cur) {                 // left a cell: hand its sum to R[theta]
+                        if (cur >= 0) red_cell<PPC>(Gt + (size_t)cur * PPC, acc);
+#pragma unroll
+                        for (int e = 0; e < PPC; ++e) acc[e] = 0;
+                        cur = c;
+                    }
+                    accumulate_outer<NDIM>(acc, lam, ps[s]);
+                    // lambda_n = M^T lambda_{n+1} = lambda_{n+1} + D^T lambda_{n+1}
+                    T nl[NDIM];
+#pragma unroll
+                    for (int r = 0; r < NDIM; ++r) {
+                        T t = lam[r];
+#pragma unroll
+                        for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(w[StepRec<NDIM>::d(j, r)], lam[j], t);
+                        nl[r] = t;
+                    }
+#pragma unroll
+                    for (int r = 0; r < NDIM; ++r) lam[r] = nl[r];
+                }
+            }
+        };
+        segment(nseg - 1, std::false_type{});
+        for (int sg = nseg - 2; sg >= 0; --sg) segment(sg, std::true_type{});
+    }
+};
+
+// the trajectory's start point and lambda_N = dL/dp_N.  SAMPLE: `gout` holds the transformed grid
+// (output of the forward) and the upstream gradient is that of the sampled image, `gimg` (fused
+// transform_data): lambda_N is formed here.
+template <typename T, int NDIM, bool SAMPLE>
+__device__ __forceinline__ void load_trajectory(const T* __restrict__ points, const T* __restrict__ gout, long nP,
+                                                int broadcast, int theta, long i, const T* __restrict__ data,
+                                                const T* __restrict__ gimg, const Shape& sh, T* p, T* lam)
+{
+    const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
+    const T* gsrc = gout + (size_t)theta * NDIM * nP;
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) { p[j] = src[i + (long)j * nP]; lam[j] = gsrc[i + (long)j * nP]; }
+    if (SAMPLE) {
+        T pt[NDIM];
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) pt[j] = lam[j];
+        sample_vjp<T, NDIM>(pt, theta, i, data, gimg, sh, lam);
+    }
 }
 
 #ifndef CPAB_BWD_REGS
@@ -222,10 +375,11 @@ template <typename T, int NDIM, int SEG, int BLOCK> struct BwdOcc {
     static constexpr int kMinBlocks = sizeof(T) == 8 ? 1 : 65536 / (BLOCK * kRegs);
 };
 
-// SAMPLE: `gout` holds the transformed grid (output of the forward) and the upstream gradient is
-// that of the sampled image, `gimg`; lambda_N is formed in the prologue (fused transform_data).
-// CERT: pass 1 carries the cell-sequence certificate and failed trajectories are re-integrated
-// with the reference's arithmetic (float32 only; see the header of this file).
+// CERT: pass 1 carries the cell-sequence certificate; a trajectory that fails it is skipped here
+// and marked in a bit mask (one 32-bit word per warp and iteration: the ballot), from which
+// k_backward_redo re-integrates it with the reference's arithmetic (float32 only; see the header
+// of this file).  Keeping that cold, conversion-bound code out of this kernel keeps its register
+// budget and its unit barriers as they are without the certificate.
 template <typename T, int NDIM, int SEG, bool SMEM, int BLOCK, bool SAMPLE, bool CERT>
 __global__ void __launch_bounds__(BLOCK, (BwdOcc<T, NDIM, SEG, BLOCK>::kMinBlocks))
 k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __restrict__ gout,
@@ -238,201 +392,194 @@ k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __re
     constexpr int PPC = Dim<NDIM>::kPpc;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned s_work;
-    __shared__ int s_nredo;
-    __shared__ float s_slope;
+    __shared__ float s_eta;
     constexpr int WS = StepRec<NDIM>::kStride;
     const int tsize = g.n_cells * PPC;
     const int wsize = g.n_cells * WS;
-    const int nseg = (nsteps + SEG - 1) / SEG;
 
     // shared layout: [step records] (if SMEM), checkpoints [nseg][NDIM][BLOCK], cell trace
     // [nsteps][BLOCK] (16-bit; 32-bit only for tessellations of >= 65536 simplices, which never
-    // fit the staged path), redo list [unit points] (16-bit offsets into the unit, CERT only)
+    // fit the staged path)
     T* sW = reinterpret_cast<T*>(smem_raw);
-    T* ck = sW + (SMEM ? wsize : 0);
-    unsigned short* ct16 = reinterpret_cast<unsigned short*>(ck + (size_t)nseg * NDIM * BLOCK);
-    int* ct32 = reinterpret_cast<int*>(ct16);
-    const bool wide = !SMEM && g.n_cells > 65535;
-    unsigned short* redo = ct16 + (size_t)nsteps * BLOCK * (wide ? 2 : 1);
+    Sweep<T, NDIM, SEG> sw;
+    sw.nsteps = nsteps;
+    sw.nseg = (nsteps + SEG - 1) / SEG;
+    sw.ck = sW + (SMEM ? wsize : 0);
+    sw.ct16 = reinterpret_cast<unsigned short*>(sw.ck + (size_t)sw.nseg * NDIM * BLOCK);
+    sw.ct32 = reinterpret_cast<int*>(sw.ct16);
+    sw.wide = !SMEM && g.n_cells > 65535;
+    sw.stride = BLOCK;
+    sw.slot = threadIdx.x;
     CellTable<T, NDIM, SMEM, WS> tab;
     tab.saddr = SMEM ? (uint32_t)__cvta_generic_to_shared(sW) & 0xffffffu : 0;   // CTA-local offset (no cluster launch: rank bits are 0)
-    int staged = -1;
-    float magic = 12582912.0f;     // 1.5 * 2^23, rounding constant of the cell search
+    float magic = 12582912.0f;        // 1.5 * 2^23, rounding constant of the cell search
     asm volatile("" : "+f"(magic));
+    int staged = -1;
     WorkUnit wu;
-    while (next_unit(wp, nP, counter, &s_work, wu)) {
+    for (;;) {
+    // ---- next work unit (all threads): drawn from the counter in the caller's workspace
+    __syncthreads();                                   // everyone is done with the previous unit
+    if (threadIdx.x == 0) s_work = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (s_work >= wp.total) break;
+    unit_of(wp, s_work, nP, wu);
     const int theta = wu.theta;
-    const long begin = wu.begin;
-    const int span = (int)(wu.end - wu.begin);
+    const long begin = wu.begin, end = wu.end;
     tab.gptr = Ws + (size_t)theta * wsize;
-    if (SMEM && theta != staged) {           // (next_unit synchronised: nobody reads the old table any more)
+    if (SMEM && theta != staged) {           // (synchronised above: nobody reads the old table any more)
         stage_block(sW, tab.gptr, wsize);
         staged = theta;
     }
-    if (CERT && threadIdx.x == 0) {
-        s_nredo = 0;
-        s_slope = cert_slope(ca, theta, nsteps);
-    }
+    if (CERT && threadIdx.x == 0) s_eta = cert_eta(ca, theta, nsteps);
     if (SMEM || CERT) __syncthreads();
-    const float slope = CERT ? s_slope : 0.0f;
+    const float eta_s = CERT ? s_eta : 0.0f;
     T* Gg = G + (size_t)theta * tsize;
     // keep the base in registers: the flush blocks run divergently, often, and would otherwise
     // rebuild it from the kernel parameters (11 uniform-datapath instructions per occurrence)
     asm volatile("" : "+l"(Gg));
-    const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
-    const T* gsrc = gout + (size_t)theta * NDIM * nP;
-    const T* Ag = CERT ? reinterpret_cast<const T*>(ca.As) + (size_t)theta * tsize : nullptr;
 
-    // phase 0: every point of the unit, record arithmetic (+ certificate);
-    // phase 1 (CERT): the trajectories whose certificate failed, reference arithmetic
-    for (int phase = 0; phase < (CERT ? 2 : 1); ++phase) {
-    const int count = phase == 0 ? span : s_nredo;
-    for (int b0 = 0; b0 < count; b0 += BLOCK) {      // warp-uniform trip count
-        const int jj = b0 + threadIdx.x;
-        const bool valid = jj < count;
+    for (long base = begin; base < end; base += BLOCK) {      // warp-uniform trip count
+        const long i = base + threadIdx.x;
+        const bool valid = i < end;
         T acc[PPC];
         int cur = -1;
+        bool failed = false;
 #pragma unroll
         for (int e = 0; e < PPC; ++e) acc[e] = 0;
         if (valid) {
-            const int off = (CERT && phase == 1) ? (int)redo[jj] : jj;
-            const long i = begin + off;
             T p[NDIM], lam[NDIM];
+            load_trajectory<T, NDIM, SAMPLE>(points, gout, nP, broadcast, theta, i, data, gimg, sh, p, lam);
+            failed = sw.template pass1<CERT ? 1 : 0>(g, tab, nullptr, ca.floor, eta_s, magic, p);
+            if (!failed) {
+                sw.pass2(tab, Gg, lam, acc, cur);
+                if (dpoints != nullptr) {
+                    T* dp = dpoints + (size_t)theta * NDIM * nP;
 #pragma unroll
-            for (int j = 0; j < NDIM; ++j) { p[j] = src[i + (long)j * nP]; lam[j] = gsrc[i + (long)j * nP]; }
-            if (SAMPLE) {       // gsrc is the transformed grid: turn it into dL/d(grid_t)
-                T pt[NDIM];
-#pragma unroll
-                for (int j = 0; j < NDIM; ++j) pt[j] = lam[j];
-                sample_vjp<T, NDIM>(pt, theta, i, data, gimg, sh, lam);
+                    for (int j = 0; j < NDIM; ++j) dp[i + (long)j * nP] = lam[j];
+                }
             }
+        }
+        flush_runs<T, PPC>(Gg, cur, acc);
+        if (CERT) {
+            // units begin at multiples of 256 points, so a warp's 32 points are exactly one mask
+            // word; a warp wholly beyond `end` owns none
+            const unsigned word = __ballot_sync(0xffffffffu, failed);
+            if ((threadIdx.x & 31) == 0 && i < end) ca.mask[(size_t)theta * ca.words + (i >> 5)] = word;
+        }
+    }
+    }   // work units
+}
 
-            // ---- pass 1: the RK2 trajectory.  Records the cell of every step and a checkpoint
-            //      of p at the start of every segment; the only pass that searches cells.
-            //      (FULL = a whole segment that is not the last one: no bounds checks.)
-            //      MODE 0: records + complete search (no certificate: float64, CPAB_FLAG_FAST_GRAD)
-            //      MODE 1: records + certified fast search; sets `failed` and stops early
-            //      MODE 2: the reference's arithmetic + complete search
-            bool failed = false;
-            float m = 0.0f;                 // certificate margin of the current step, n * slope
-            int c_first = 0;
-            auto pass1 = [&](int sg, auto full_tag, auto mode_tag) {
-                constexpr bool FULL = decltype(full_tag)::value;
-                constexpr int MODE = decltype(mode_tag)::value;
-#pragma unroll
-                for (int j = 0; j < NDIM; ++j) ck[(sg * NDIM + j) * BLOCK + threadIdx.x] = p[j];
-#pragma unroll
-                for (int s = 0; s < SEG; ++s) {
-                    const int n = sg * SEG + s;
-                    if (FULL || n < nsteps) {
-                        int c;
-                        if constexpr (MODE == 1) {
-                            float dist;
-                            c = find_cell_near<NDIM>(p, g, magic, dist);
-                            if (s == 0 && sg == 0) { c = c_first; dist = 1.0f; }   // step 0: identical input, complete search
-                            failed |= dist < m;
-                            m += slope;
-                        } else {
-                            c = find_cell<NDIM>(p, g);
-                        }
-                        if (wide) ct32[n * BLOCK + threadIdx.x] = c;
-                        else ct16[n * BLOCK + threadIdx.x] = (unsigned short)c;
-                        if (FULL || n + 1 < nsteps) {
-                            if constexpr (MODE == 2) {
-                                T a[PPC];
-                                load_affine<NDIM>(Ag + (size_t)c * PPC, a);
-                                step_reference<NDIM>(a, 1.0 / nsteps, p);
-                            } else {
-                                T w[WS];
-                                tab.load(c, w);
-                                step_inc<NDIM>(w, p);
-                            }
-                        }
-                    }
-                }
-            };
-            if (!CERT) {
-                for (int sg = 0; sg + 1 < nseg; ++sg) pass1(sg, std::true_type{}, std::integral_constant<int, 0>{});
-                pass1(nseg - 1, std::false_type{}, std::integral_constant<int, 0>{});
-            } else if (phase == 0) {
-                c_first = find_cell<NDIM>(p, g);
-                int sg = 0;
-                for (; sg + 1 < nseg && !failed; ++sg) pass1(sg, std::true_type{}, std::integral_constant<int, 1>{});
-                if (sg + 1 == nseg && !failed) pass1(nseg - 1, std::false_type{}, std::integral_constant<int, 1>{});
-            } else {
-                for (int sg = 0; sg + 1 < nseg; ++sg) pass1(sg, std::true_type{}, std::integral_constant<int, 2>{});
-                pass1(nseg - 1, std::false_type{}, std::integral_constant<int, 2>{});
-            }
+// Re-integration of the trajectories whose certificate failed, with the reference's arithmetic.
+// Every warp is an independent worker: it draws chunks of 8 mask words (256 trajectories of one
+// theta) from a counter, expands the set bits into a list in shared memory and, whenever 32 are
+// waiting, integrates them as one full-width iteration -- pass 1 in mode 2 (the reference's float
+// A p~ and double-rounded updates, complete cell search), pass 2 as in k_backward but with the step
+// records of each lane's own theta read through L1.  The loop is bound by the latency of the
+// F2F.F64<->F32 conversions (16 lanes/clk/SM); it touches a few per cent of the trajectories.
+// 6 CTAs x 128 threads per SM (80 registers): 4 CTAs (109 registers, no spills) run as fast, 8 (64
+// registers) spill and run 30 % slower; chunks of 4 mask words: 1 or 2 cost more draws than they
+// save in tail (0.69 / 0.77 / 1.01 ms for 4 / 2 / 1 words on 128 thetas x 512^2)
+#ifndef CPAB_REDO_CTAS
+#define CPAB_REDO_CTAS 6
+#endif
+#ifndef CPAB_REDO_CHUNK
+#define CPAB_REDO_CHUNK 4
+#endif
+constexpr int kRedoChunkWords = CPAB_REDO_CHUNK;
+template <int NDIM, int SEG, bool SAMPLE>
+__global__ void __launch_bounds__(128, CPAB_REDO_CTAS)
+k_backward_redo(const float* __restrict__ points, const float* __restrict__ Ws, const float* __restrict__ gout,
+                float* __restrict__ G, float* __restrict__ dpoints, long nP, int broadcast, int nsteps,
+                int n_theta, const __grid_constant__ Geom g, unsigned* __restrict__ counter,
+                const float* __restrict__ data, const float* __restrict__ gimg, const __grid_constant__ Shape sh,
+                const __grid_constant__ CertArgs ca)
+{
+    using T = float;
+    constexpr int PPC = Dim<NDIM>::kPpc;
+    constexpr int WS = StepRec<NDIM>::kStride;
+    constexpr int kChunkWords = kRedoChunkWords;
+    constexpr int kListCap = 31 + 32 * kChunkWords;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tsize = g.n_cells * PPC;
+    const int wsize = g.n_cells * WS;
+    Sweep<T, NDIM, SEG> sw;
+    sw.nsteps = nsteps;
+    sw.nseg = (nsteps + SEG - 1) / SEG;
+    sw.wide = g.n_cells > 65535;
+    sw.stride = 32;
+    sw.slot = lane;
+    // per warp: list [kListCap] x (theta, point) | checkpoints [nseg][NDIM][32] | cell trace [nsteps][32]
+    const size_t per_warp = (((size_t)kListCap * 8 + (size_t)sw.nseg * NDIM * 32 * 4 +
+                              (size_t)nsteps * 32 * (sw.wide ? 4 : 2)) + 15) & ~(size_t)15;
+    unsigned char* mine = smem_raw + per_warp * warp;
+    uint2* list = reinterpret_cast<uint2*>(mine);
+    sw.ck = reinterpret_cast<T*>(mine + (size_t)kListCap * 8);
+    sw.ct16 = reinterpret_cast<unsigned short*>(sw.ck + (size_t)sw.nseg * NDIM * 32);
+    sw.ct32 = reinterpret_cast<int*>(sw.ct16);
+    const long chunks_per_theta = (ca.words + kChunkWords - 1) / kChunkWords;
+    const long total = chunks_per_theta * n_theta;
+    int n_list = 0;                   // warp-uniform
 
-            if (CERT && failed) {
-                redo[atomicAdd(&s_nredo, 1)] = (unsigned short)off;
-            } else {
-            // ---- pass 2: segments in reverse; replay p into registers (no search), sweep back
-            auto pass2 = [&](int sg, auto full_tag) {
-                constexpr bool FULL = decltype(full_tag)::value;
-                const int len = FULL ? SEG : nsteps - sg * SEG;
-                T ps[SEG][NDIM];
-                T w[WS];
-                int cs[SEG];
+    auto redo = [&](int first, int n) {
+        if (lane < n) {
+            const uint2 e = list[first + lane];
+            const int theta = (int)e.x;
+            const long i = (long)e.y;
+            T p[NDIM], lam[NDIM], acc[PPC];
+            int cur = -1;
 #pragma unroll
-                for (int j = 0; j < NDIM; ++j) p[j] = ck[(sg * NDIM + j) * BLOCK + threadIdx.x];
-#pragma unroll
-                for (int s = 0; s < SEG; ++s) {
-                    if (FULL || s < len) {
-                        const int n = sg * SEG + s;
-                        cs[s] = wide ? ct32[n * BLOCK + threadIdx.x] : (int)ct16[n * BLOCK + threadIdx.x];
-#pragma unroll
-                        for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
-                        if (s + 1 < SEG && (FULL || s + 1 < len)) {
-                            tab.load(cs[s], w);       // (the compiler keeps these for the sweep below)
-                            step_inc<NDIM>(w, p);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int s = SEG - 1; s >= 0; --s) {
-                    if (FULL || s < len) {
-                        const int c = cs[s];
-                        tab.load(c, w);
-                        if (c != cur) {                 // left a cell: hand its sum to R[theta]
-                            if (cur >= 0) red_cell<PPC>(Gg + (size_t)cur * PPC, acc);
-#pragma unroll
-                            for (int e = 0; e < PPC; ++e) acc[e] = 0;
-                            cur = c;
-                        }
-                        // R_c += lambda_{n+1} [p_n;1]^T
-                        accumulate_outer<NDIM>(acc, lam, ps[s]);
-                        // lambda_n = M^T lambda_{n+1} = lambda_{n+1} + D^T lambda_{n+1}
-                        T nl[NDIM];
-#pragma unroll
-                        for (int r = 0; r < NDIM; ++r) {
-                            T t = lam[r];
-#pragma unroll
-                            for (int j = 0; j < NDIM; ++j) t = Num<T>::fma(w[StepRec<NDIM>::d(j, r)], lam[j], t);
-                            nl[r] = t;
-                        }
-#pragma unroll
-                        for (int r = 0; r < NDIM; ++r) lam[r] = nl[r];
-                    }
-                }
-            };
-            pass2(nseg - 1, std::false_type{});
-            for (int sg = nseg - 2; sg >= 0; --sg) pass2(sg, std::true_type{});
+            for (int k = 0; k < PPC; ++k) acc[k] = 0;
+            load_trajectory<T, NDIM, SAMPLE>(points, gout, nP, broadcast, theta, i, data, gimg, sh, p, lam);
+            CellTable<T, NDIM, false, WS> gtab;      // this lane's theta: records through L1
+            gtab.gptr = Ws + (size_t)theta * wsize;
+            gtab.saddr = 0;
+            const T* Ag = reinterpret_cast<const T*>(ca.As) + (size_t)theta * tsize;
+            sw.template pass1<2>(g, gtab, Ag, 0.0f, 0.0f, 0.0f, p);
+            T* Gt = G + (size_t)theta * tsize;
+            sw.pass2(gtab, Gt, lam, acc, cur);
             if (dpoints != nullptr) {
                 T* dp = dpoints + (size_t)theta * NDIM * nP;
 #pragma unroll
                 for (int j = 0; j < NDIM; ++j) dp[i + (long)j * nP] = lam[j];
             }
-            }
+            if (cur >= 0) red_cell<PPC>(Gt + (size_t)cur * PPC, acc);
+            if (ca.flagged != nullptr) atomicAdd(ca.flagged + theta, 1);
         }
-        flush_runs<T, PPC>(Gg, cur, acc);
+        __syncwarp();
+    };
+
+    for (;;) {
+        long chunk = 0;
+        if (lane == 0) chunk = (long)atomicAdd(counter, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= total) break;
+        const int theta = (int)(chunk / chunks_per_theta);
+        const long w0 = (chunk - (long)theta * chunks_per_theta) * kChunkWords;
+        unsigned word = 0;
+        if (lane < kChunkWords && w0 + lane < ca.words) word = ca.mask[(size_t)theta * ca.words + w0 + lane];
+        // exclusive prefix of the bit counts over the (8) loading lanes
+        const int cnt = __popc(word);
+        int pre = cnt;
+#pragma unroll
+        for (int off = 1; off < kChunkWords; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, pre, off);
+            if (lane >= off) pre += t;
+        }
+        const int all = __shfl_sync(0xffffffffu, pre, kChunkWords - 1);
+        if (all == 0) continue;
+        int at = n_list + pre - cnt;
+        while (word != 0) {
+            const int b = __ffs(word) - 1;
+            word &= word - 1;
+            list[at++] = make_uint2((unsigned)theta, (unsigned)((w0 + lane) * 32 + b));
+        }
+        n_list += all;
+        __syncwarp();
+        while (n_list >= 32) { n_list -= 32; redo(n_list, 32); }
     }
-    if (CERT) {
-        __syncthreads();       // phase 0: the list is complete; phase 1: it has been consumed
-        if (phase == 0 && ca.flagged != nullptr && threadIdx.x == 0 && s_nredo > 0) atomicAdd(ca.flagged + theta, s_nredo);
-    }
-    }   // phases
-    }   // work units
+    if (n_list > 0) redo(0, n_list);
 }
 
 // Per (theta, cell): the RK2 step record (see step_inc) from A_c = [L | t], and a zeroed R_c block.
@@ -557,9 +704,9 @@ k_rk2_trace(const float* __restrict__ points, const float* __restrict__ As, cons
     float p[NDIM];
 #pragma unroll
     for (int j = 0; j < NDIM; ++j) p[j] = src[i + (long)j * nP];
-    CertArgs ca{As, stats, cert_scale(g), cert_floor(g), nullptr};
-    const float slope = mode == 1 ? cert_slope(ca, theta, nsteps) : 0.0f;
-    float m = 0.0f;
+    CertArgs ca{As, stats, cert_scale(g), cert_floor(g), nullptr, 0, nullptr};
+    const float eta_s = mode == 1 ? cert_eta(ca, theta, nsteps) : 0.0f;
+    float m = ca.floor;
     bool failed = false;
     const float magic = 12582912.0f;
     int* out = cells + (size_t)theta * nsteps * nP + i;
@@ -572,7 +719,6 @@ k_rk2_trace(const float* __restrict__ points, const float* __restrict__ As, cons
         } else {
             c = find_cell<NDIM>(p, g);
         }
-        m += slope;
         out[(size_t)n * nP] = c;
         if (mode == 2) {
             float a[PPC];
@@ -583,6 +729,7 @@ k_rk2_trace(const float* __restrict__ points, const float* __restrict__ As, cons
 #pragma unroll
             for (int e = 0; e < WS; ++e) w[e] = Ws[((size_t)theta * g.n_cells + c) * WS + e];
             step_inc<NDIM>(w, p);
+            m = fmaf(m, cert_gain<NDIM>(w), m + eta_s);
         }
     }
     if (failed_out != nullptr) failed_out[(size_t)theta * nP + i] = failed ? 1 : 0;
@@ -593,19 +740,23 @@ k_rk2_trace(const float* __restrict__ points, const float* __restrict__ As, cons
 // =====================================================================================================
 // workspace layout (all offsets 16-byte aligned):
 //   G [n_theta, D] (accumulated as R, converted in place) | step records W [n_theta, nC, stride] |
-//   certificate stats [n_theta][2] float | work counters [4] unsigned
+//   certificate stats [n_theta][2] float | work counters [4] unsigned |
+//   (float32) failed-certificate mask [n_theta][ceil(nP/32)] unsigned
 struct BwdLayout {
-    size_t off_w, off_stats, off_counter, total;
+    size_t off_w, off_stats, off_counter, off_mask, total;
+    long words;
 };
 template <int NDIM>
-inline BwdLayout backward_layout(size_t elt, const Geom& g, int n_theta)
+inline BwdLayout backward_layout(size_t elt, const Geom& g, int n_theta, long nP)
 {
     auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
     BwdLayout l;
     l.off_w = up((size_t)n_theta * g.n_cells * Dim<NDIM>::kPpc * elt);
     l.off_stats = up(l.off_w + (size_t)n_theta * g.n_cells * StepRec<NDIM>::kStride * elt);
     l.off_counter = up(l.off_stats + (size_t)n_theta * 2 * sizeof(float));
-    l.total = l.off_counter + 16;
+    l.off_mask = l.off_counter + 16;
+    l.words = (nP + 31) / 32;
+    l.total = up(l.off_mask + (elt == 4 ? (size_t)n_theta * l.words * 4 : 0));
     return l;
 }
 
@@ -617,10 +768,8 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
 {
     const int nseg = (nsteps + SEG - 1) / SEG;
     const size_t tbytes = (size_t)g.n_cells * StepRec<NDIM>::kStride * sizeof(T);
-    const Tuning& tn = tuning();
-    const int unit_max = tn.chunk_pts > 256 ? tn.chunk_pts : 256;
     const size_t smem = (SMEM ? tbytes : 0) + (size_t)nseg * NDIM * BLOCK * sizeof(T) +
-                        (size_t)nsteps * BLOCK * (g.n_cells > 65535 ? 4 : 2) + (CERT ? (size_t)unit_max * 2 : 0);
+                        (size_t)nsteps * BLOCK * (g.n_cells > 65535 ? 4 : 2);
     fits = smem <= kMaxSmemBytes;
     if (!fits) return kOk;
     auto launch = [&](auto kern, const SampleArgs& a) -> int {
@@ -628,7 +777,7 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
             CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
-        if ((long long)n_theta * ((nP + 255) / 256) > 0x7fffffffLL) { set_error("grid too large"); return kErrUnsupported; }
+        if ((long long)n_theta * ((nP + 255) / 256) > 0x7fffffffLL || nP >= (1L << 32)) { set_error("grid too large"); return kErrUnsupported; }
         unsigned blocks = 0;
         const WorkPlan wp = plan_work(nP, n_theta, BLOCK, per_sm, blocks, true);
         prof_begin(kProfBackward, st);
@@ -646,6 +795,43 @@ static int backward_launch(const Geom& g, int nsteps, int n_theta, long nP, int 
     return kOk;
 }
 
+// second kernel of the certified mode: the marked trajectories, reference arithmetic
+template <int NDIM, int SEG>
+static int redo_launch(const Geom& g, int nsteps, int n_theta, long nP, int broadcast, const void* points,
+                       const void* Ws, const void* gout, void* G, void* dpoints, unsigned* counter,
+                       const CertArgs& ca, cudaStream_t st, bool& fits, const SampleArgs* sa)
+{
+    const int nseg = (nsteps + SEG - 1) / SEG;
+    const size_t per_warp = (((size_t)(31 + 32 * kRedoChunkWords) * 8 + (size_t)nseg * NDIM * 32 * 4 +
+                              (size_t)nsteps * 32 * (g.n_cells > 65535 ? 4 : 2)) + 15) & ~(size_t)15;
+    int warps = 4;
+    while (warps > 1 && per_warp * warps > kMaxSmemBytes) warps /= 2;
+    fits = per_warp * warps <= kMaxSmemBytes;
+    if (!fits) return kOk;
+    const size_t smem = per_warp * warps;
+    auto launch = [&](auto kern, const SampleArgs& a) -> int {
+        if (smem > 48 * 1024)
+            CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem);
+        const long chunks = ((ca.words + kRedoChunkWords - 1) / kRedoChunkWords) * n_theta;
+        long blocks = (long)sm_count() * (per_sm > 0 ? per_sm : 1);
+        if (blocks * warps > chunks) blocks = (chunks + warps - 1) / warps;
+        prof_begin(kProfBackwardRedo, st);
+        kern<<<(unsigned)blocks, 32 * warps, smem, st>>>((const float*)points, (const float*)Ws, (const float*)gout,
+                                                         (float*)G, (float*)dpoints, nP, broadcast, nsteps, n_theta, g,
+                                                         counter, (const float*)a.data, (const float*)a.gimg, a.sh, ca);
+        prof_end(kProfBackwardRedo, st);
+        count_launch();
+        return kOk;
+    };
+    const int rc = sa != nullptr ? launch(k_backward_redo<NDIM, SEG, true>, *sa)
+                                 : launch(k_backward_redo<NDIM, SEG, false>, SampleArgs());
+    if (rc != kOk) return rc;
+    CPAB_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
 template <typename T, int NDIM, bool CERT>
 static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, int broadcast,
                       const void* points, const void* As, const void* basis, const void* gout,
@@ -653,7 +839,7 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
 {
     const int D = g.n_cells * Dim<NDIM>::kPpc;
     const long n_blocks = (long)n_theta * g.n_cells;
-    const BwdLayout lay = backward_layout<NDIM>(sizeof(T), g, n_theta);
+    const BwdLayout lay = backward_layout<NDIM>(sizeof(T), g, n_theta, nP);
     char* base = reinterpret_cast<char*>(ws);
     T* Ws = reinterpret_cast<T*>(base + lay.off_w);
     float* stats = CERT ? reinterpret_cast<float*>(base + lay.off_stats) : nullptr;
@@ -662,7 +848,7 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
     k_prepare_backward<T, NDIM><<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>((const T*)As, Ws, (T*)ws, n_blocks, nsteps, g, counter, stats);
     CPAB_CUDA_OK(cudaGetLastError());
     count_launch();
-    CertArgs ca{As, stats, cert_scale(g), cert_floor(g), flagged};
+    CertArgs ca{As, stats, cert_scale(g), cert_floor(g), reinterpret_cast<unsigned*>(base + lay.off_mask), lay.words, flagged};
     bool fits = nP == 0;      // nothing to integrate: G stays zero, the epilogue writes dtheta = 0
     int rc = kOk;
 #define TRY(SEG, SMEM, BLOCK)                                                                      \
@@ -702,6 +888,19 @@ static int backward_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
         set_error("backward: nstepsolver=%d needs more checkpoint memory than one CTA has", nsteps);
         return kErrUnsupported;
     }
+    if constexpr (CERT) {
+        if (nP > 0) {
+            bool rfits = false;
+            rc = redo_launch<NDIM, 5>(g, nsteps, n_theta, nP, broadcast, points, Ws, gout, ws, dpoints, counter + 1, ca, st, rfits, sa);
+            if (rc == kOk && !rfits)
+                rc = redo_launch<NDIM, 10>(g, nsteps, n_theta, nP, broadcast, points, Ws, gout, ws, dpoints, counter + 1, ca, st, rfits, sa);
+            if (rc != kOk) return rc;
+            if (!rfits) {
+                set_error("backward: nstepsolver=%d needs more checkpoint memory than one CTA has", nsteps);
+                return kErrUnsupported;
+            }
+        }
+    }
     {
         k_r_to_g<T, NDIM><<<(unsigned)((n_blocks + 255) / 256), 256, 0, st>>>((T*)ws, (const T*)As, n_blocks, nsteps);
         CPAB_CUDA_OK(cudaGetLastError());
@@ -732,7 +931,7 @@ int rk2_trace_dim_impl(const Geom& g, int nsteps, int n_theta, long nP, int broa
                        cudaStream_t st)
 {
     const long n_blocks = (long)n_theta * g.n_cells;
-    const BwdLayout lay = backward_layout<NDIM>(sizeof(float), g, n_theta);
+    const BwdLayout lay = backward_layout<NDIM>(sizeof(float), g, n_theta, nP);
     char* base = reinterpret_cast<char*>(ws);
     float* Ws = reinterpret_cast<float*>(base + lay.off_w);
     float* stats = reinterpret_cast<float*>(base + lay.off_stats);

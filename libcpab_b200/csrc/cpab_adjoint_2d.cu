@@ -20,9 +20,9 @@ int rk2_trace_dim_2(const Geom& g, int nsteps, int n_theta, long nP, int broadca
     return rk2_trace_dim_impl<2>(g, nsteps, n_theta, nP, broadcast, mode, points, As, ws, cells, failed, st);
 }
 
-size_t backward_workspace_bytes_2(size_t elt, const Geom& g, int n_theta)
+size_t backward_workspace_bytes_2(size_t elt, const Geom& g, int n_theta, long nP)
 {
-    return backward_layout<2>(elt, g, n_theta).total;
+    return backward_layout<2>(elt, g, n_theta, nP).total;
 }
 #endif
 

@@ -529,12 +529,13 @@ CPAB_HD float cert_scale(const Geom& g)
     for (int j = 0; j < g.ndim; ++j) s += g.nf[j];
     return s;
 }
-// floor of every certificate margin: the guard band of the fast search itself
+// M_0 of the certificate: the guard band of the fast search itself, plus one ulp of the unit box
+// in local units (an iterate whose pre-rounding value reaches the domain boundary is then flagged)
 CPAB_HD float cert_floor(const Geom& g)
 {
-    return g.ndim == 1 ? 4.0f * 5.9604645e-08f * g.nf[0] : g.ndim == 2 ? g.band2 : 4e-6f;
+    const float band = g.ndim == 1 ? 4.0f * 5.9604645e-08f * g.nf[0] : g.ndim == 2 ? g.band2 : 4e-6f;
+    return band + 1.1920929e-07f * cert_scale(g);
 }
-
 CPAB_HD int find_cell_3d_near(float p0, float p1, float p2, const Geom& g, float& dist)
 {
     int cell;

@@ -36,7 +36,7 @@ void set_error(const char* fmt, ...);
 // `gpu_launches`.  When profiling is switched on (cpab_b200_profile_enable), the dominant kernels
 // are bracketed by CUDA events on their own stream and the elapsed time is accumulated per slot.
 enum ProfSlot : int { kProfForward = 0, kProfBackward = 1, kProfInterpFwd = 2, kProfInterpBwd = 3,
-                      kProfThetaToTrels = 4, kProfEpilogue = 5, kProfSlots = 6 };
+                      kProfThetaToTrels = 4, kProfEpilogue = 5, kProfBackwardRedo = 6, kProfSlots = 7 };
 void count_launch(int n = 1);
 bool prof_begin(int slot, cudaStream_t st);   // true if an event was recorded
 void prof_end(int slot, cudaStream_t st);
@@ -70,7 +70,7 @@ int launch_jacobian(int dtype, const Geom& g, int nsteps, int n_theta, int d, lo
                     int broadcast, const void* points, const void* As, const void* Bs, void* jac,
                     cudaStream_t st);
 size_t backward_g_bytes(int dtype, const Geom& g, int n_theta);           // G [n_theta, D]
-size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta);   // G + RK2 step table
+size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta, long nP);   // G + RK2 step table + certificate scratch
 int launch_backward(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int d, long nP,
                     int broadcast, const void* points, const void* As, const void* basis,
                     const void* grad_out, void* dtheta, void* dpoints, void* workspace,

@@ -523,7 +523,7 @@ int launch_grad_epilogue(int dtype, const void* G, const void* basis, void* dthe
     int rk2_trace_dim_##N(const Geom& g, int nsteps, int n_theta, long nP, int broadcast, int mode, \
                           const void* points, const void* As, void* ws, int* cells,                 \
                           unsigned char* failed, cudaStream_t st);                                  \
-    size_t backward_workspace_bytes_##N(size_t elt, const Geom& g, int n_theta);
+    size_t backward_workspace_bytes_##N(size_t elt, const Geom& g, int n_theta, long nP);
 CPAB_DECL_DIM(1)
 CPAB_DECL_DIM(2)
 CPAB_DECL_DIM(3)
@@ -534,11 +534,11 @@ size_t backward_g_bytes(int dtype, const Geom& g, int n_theta)
     const size_t elt = dtype == kF32 ? 4 : 8;
     return (size_t)n_theta * g.n_cells * g.ndim * (g.ndim + 1) * elt;
 }
-size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta)
+size_t backward_workspace_bytes(int dtype, const Geom& g, int n_theta, long nP)
 {
     const size_t elt = dtype == kF32 ? 4 : 8;
-    return CPAB_DISPATCH(backward_workspace_bytes_1(elt, g, n_theta), backward_workspace_bytes_2(elt, g, n_theta),
-                         backward_workspace_bytes_3(elt, g, n_theta));
+    return CPAB_DISPATCH(backward_workspace_bytes_1(elt, g, n_theta, nP), backward_workspace_bytes_2(elt, g, n_theta, nP),
+                         backward_workspace_bytes_3(elt, g, n_theta, nP));
 }
 
 static int backward_any(int dtype, int flags, const Geom& g, int nsteps, int n_theta, int d, long nP,
@@ -546,8 +546,8 @@ static int backward_any(int dtype, int flags, const Geom& g, int nsteps, int n_t
                         const void* gout, void* dtheta, void* dpoints, void* ws, size_t ws_bytes,
                         int* flagged, cudaStream_t st, const SampleArgs* sa)
 {
-    if (ws_bytes < backward_workspace_bytes(dtype, g, n_theta)) {
-        set_error("backward: workspace has %zu bytes, needs %zu", ws_bytes, backward_workspace_bytes(dtype, g, n_theta));
+    if (ws_bytes < backward_workspace_bytes(dtype, g, n_theta, nP)) {
+        set_error("backward: workspace has %zu bytes, needs %zu", ws_bytes, backward_workspace_bytes(dtype, g, n_theta, nP));
         return kErrWorkspace;
     }
     if (reinterpret_cast<uintptr_t>(ws) & 15) { set_error("backward: workspace must be 16-byte aligned"); return kErrArgument; }
@@ -571,7 +571,7 @@ int launch_rk2_trace(const Geom& g, int nsteps, int n_theta, long nP, int broadc
                      int* cells, unsigned char* failed, cudaStream_t st)
 {
     if (n_theta == 0 || nP == 0) return kOk;
-    if (workspace_bytes < backward_workspace_bytes(kF32, g, n_theta)) { set_error("rk2_trace: workspace too small"); return kErrWorkspace; }
+    if (workspace_bytes < backward_workspace_bytes(kF32, g, n_theta, nP)) { set_error("rk2_trace: workspace too small"); return kErrWorkspace; }
     if (reinterpret_cast<uintptr_t>(workspace) & 15) { set_error("rk2_trace: workspace must be 16-byte aligned"); return kErrArgument; }
 #define ARGS g, nsteps, n_theta, nP, broadcast, mode, points, As, workspace, cells, failed, st
     return CPAB_DISPATCH(rk2_trace_dim_1(ARGS), rk2_trace_dim_2(ARGS), rk2_trace_dim_3(ARGS));

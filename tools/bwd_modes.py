@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from libcpab_b200 import Cpab, ops                     # noqa: E402
+from libcpab_b200 import Cpab, _lib, ops               # noqa: E402
 from libcpab_b200.transformer import _basis            # noqa: E402
 
 CFGS = {
@@ -52,6 +52,16 @@ for name in (sys.argv[1:] or list(CFGS)):
     for fast in (False, True):
         ms = timeit(lambda: ops.backward_theta(grid, As, B, gout, tess, 50, fast_grad=fast))
         rec["bwd_fast_ms" if fast else "bwd_default_ms"] = ms
+    for fast in (False, True):          # kernel-level split (events on the launch stream, inside the library)
+        _lib.profile_enable(True)
+        for _ in range(3):
+            ops.backward_theta(grid, As, B, gout, tess, 50, fast_grad=fast)
+        torch.cuda.synchronize()
+        for slot in ("backward", "backward_redo", "epilogue"):
+            ms, n = _lib.profile_read(slot)
+            if n:
+                rec["k_%s_%s_ms" % (slot, "fast" if fast else "default")] = round(ms / n, 4)
+        _lib.profile_enable(False)
     rec["bwd_default_tflops"] = pairs * F_BWD[len(tess)] / rec["bwd_default_ms"] / 1e9
     rec["bwd_fast_tflops"] = pairs * F_BWD[len(tess)] / rec["bwd_fast_ms"] / 1e9
     rec["fwd_tflops"] = pairs * F_FWD[len(tess)] / rec["fwd_ms"] / 1e9

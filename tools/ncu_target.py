@@ -37,5 +37,6 @@ for _ in range(reps):
     out = ops.interpolate_forward(data, gt, size)
     ops.interpolate_backward(data, gt, g2, True, False)
     ops.backward_theta(grid, As, B, gout, tess, 50)
+    ops.backward_theta(grid, As, B, gout, tess, 50, fast_grad=True)
 torch.cuda.synchronize()
 print("done", which)
