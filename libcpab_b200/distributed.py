@@ -8,6 +8,12 @@ unchanged single-GPU kernels on its shard, and NO collective is issued on the fo
 A collective is needed only where a parameter is SHARED across shards (alignment / training
 mode): then the per-rank gradient of that parameter is summed with one all-reduce, enqueued on
 the compute stream right after the gradient epilogue.
+
+Secondary split, for few thetas on a huge grid (BASELINE configs[3], 16 thetas x 128^3): the POINTS
+of the one problem are split over the ranks (`PointShardedCpab`).  Every rank integrates and
+samples its slab for all thetas; the theta-gradient is a sum over points, so one all-reduce of
+dtheta [n_theta, d] completes it (14 KB for configs[3]; all-reducing the per-cell G [n_theta, D]
+instead would move 245 KB and repeat the G.B epilogue on every rank -- SURVEY.md 8-e).
 """
 from __future__ import annotations
 
@@ -96,3 +102,68 @@ class ShardedCpab:
 
     def transform_data(self, data, theta, outsize):
         return self.T.transform_data(self._local(data), self._local(theta), outsize)
+
+
+class PointShardedCpab:
+    """Point-sharded `transform_grid` / `transform_data` of ONE problem over the ranks.
+
+    The output grid `uniform_meshgrid(outsize)` is ordered first-coordinate-fastest, so a slab of
+    the LAST output dimension is a contiguous range of points, and the matching slab of the
+    sampled output `[N, C, ..., outsize[-1]]` is what `interpolate` produces for the local output
+    size `[..., slab]`.  No collective on the forward path; `allreduce_theta_grad_` sums the
+    partial theta-gradients after backward (the only collective).  `rank` / `world_size` default
+    to the process group's; passing them explicitly lets one process play every rank (tests).
+    """
+
+    def __init__(self, T, rank: int = None, world_size: int = None):
+        self.T = T
+        r, ws = world()
+        self.rank = r if rank is None else int(rank)
+        self.world_size = ws if world_size is None else int(world_size)
+
+    def slab_bounds(self, outsize):
+        """[lo, hi) of the last output dimension owned by this rank."""
+        return shard_bounds(int(outsize[-1]), self.rank, self.world_size)
+
+    def point_bounds(self, outsize):
+        """[lo, hi) of the meshgrid points owned by this rank."""
+        stride = 1
+        for v in outsize[:-1]:
+            stride *= int(v)
+        lo, hi = self.slab_bounds(outsize)
+        return lo * stride, hi * stride
+
+    def local_outsize(self, outsize):
+        lo, hi = self.slab_bounds(outsize)
+        return [int(v) for v in outsize[:-1]] + [hi - lo]
+
+    def local_grid(self, outsize):
+        lo, hi = self.point_bounds(outsize)
+        return self.T.uniform_meshgrid(outsize)[:, lo:hi].contiguous()
+
+    def transform_grid_local(self, theta, outsize):
+        """[n_theta, ndim, local points]: this rank's slab of transform_grid(uniform_meshgrid)."""
+        return self.T.transform_grid(self.local_grid(outsize), theta)
+
+    def transform_data_local(self, data, theta, outsize):
+        """[N, C, *outsize[:-1], slab]: this rank's slab of Cpab.transform_data(data, theta, outsize)."""
+        grid_t = self.transform_grid_local(theta, outsize)
+        return self.T.interpolate(data, grid_t, self.local_outsize(outsize))
+
+    def allreduce_theta_grad_(self, theta: torch.Tensor) -> torch.Tensor:
+        """Sum the partial dL/dtheta [n_theta, d] of the point shards (in place)."""
+        if theta.grad is not None and self.world_size > 1 and dist.is_available() and dist.is_initialized():
+            dist.all_reduce(theta.grad, op=dist.ReduceOp.SUM)
+        return theta
+
+    def gather_data(self, out_local: torch.Tensor, outsize) -> torch.Tensor:
+        """Concatenate the slabs of every rank along the last dimension (verification only)."""
+        if self.world_size == 1 or not (dist.is_available() and dist.is_initialized()):
+            return out_local
+        sizes = [shard_bounds(int(outsize[-1]), r, self.world_size) for r in range(self.world_size)]
+        biggest = max(hi - lo for lo, hi in sizes)
+        pad = torch.zeros(tuple(out_local.shape[:-1]) + (biggest,), dtype=out_local.dtype, device=out_local.device)
+        pad[..., :out_local.shape[-1]] = out_local
+        parts = [torch.empty_like(pad) for _ in range(self.world_size)]
+        dist.all_gather(parts, pad)
+        return torch.cat([p[..., :hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=-1)

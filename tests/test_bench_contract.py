@@ -27,7 +27,8 @@ def test_reference_arm_prints_one_valid_line():
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["metric"] == "pairs_per_s_fwd_bwd" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
-    assert d["config"]["workload"].startswith("cfg2_2d_t3x3") and "model" not in d["config"]
+    assert d["config"]["workload"].startswith("cfg3_2d_t10x10vp") and "model" not in d["config"]
+    assert d["steps"] == 1 and d["warmup"] == 0          # the arm runs the requested steps and warm-up
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

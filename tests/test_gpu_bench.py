@@ -10,20 +10,45 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_gpu_arm_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3",
-                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900)
+def _run(*args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
-    d = json.loads(lines[0])
+    return json.loads(lines[0])
+
+
+def test_gpu_arm_line():
+    """Main line on the (smaller) configs[1] workload with every extra record switched on."""
+    d = _run("--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--workload", "cfg2_2d_t3x3_b64_256x256")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "roofline_interp", "clocks",
+              "fast_grad", "alignment_cfg5", "other_workloads"):
         assert k in d, k
     assert d["steps"] == 3 and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
-    assert d["gpu_launches"] >= 3 * 5      # theta->Trels, fused forward, fused adjoint, R->G, G.B
+    assert d["gpu_launches"] >= 3 * 5      # theta->Trels, forward, adjoint (+ re-integration), R->G, G.B
     r = d["roofline"]
     assert r["bound"] == "fp32" and 0 < r["frac"] < 1.2 and r["unit"] == "TFLOP/s" and 50 < r["peak"] < 90
-    assert d["roofline_interp"]["bound"] == "hbm" and 0 < d["roofline_interp"]["frac"] < 1.2
+    # frac is reproducible from the line: pairs * flops / (ms of the three kernels) / peak
+    pairs = 64 * 256 * 256
+    assert abs(r["frac"] - pairs * r["algorithmic_flops_per_pair"] / (r["ms_per_step"] * 1e-3) / 1e12 / r["peak"]) < 1e-9
+    assert set(r["kernels"]) == {"k_forward", "k_backward+redo"}
+    ri = d["roofline_interp"]
+    assert ri["bound"] == "hbm" and 0 < ri["hbm_sized"]["k_interp_fwd"]["frac"] < 1.2 and 0 < ri["hbm_sized"]["k_interp_bwd"]["frac"] < 1.2
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 64 * 34 * 4 + 64 * 256 * 256 * 4 and e["d2h_bytes_per_step"] > 0
+    a = d["alignment_cfg5"]
+    assert a["value"] > 0 and a["e2e"]["value"] > 0 and a["allreduce_ms"] == 0.0 and a["config"]["warps"] == 4
+    assert set(d["other_workloads"]) == {"cfg1_1d_t50_b64_1000", "cfg3_2d_t10x10vp_b512_512x512",
+                                         "cfg4_3d_t4x4x4_b16_128cubed", "cfg5_1d_t100_b8192_1024"}
+    assert d["fast_grad"]["ms_per_step"] > 0
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libcpab_ref_cuda.so")):
+        v = d["vs_reference_cuda"]
+        assert v["forward"]["speedup"] > 1 and v["backward"]["speedup"] > 1 and v["forward"]["outputs_agree_1e-4"]
+        assert v["backward"]["gradient_rel_diff"] < 1e-3
+
+
+def test_default_workload_is_the_largest_single_gpu_config():
+    d = _run("--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-extras")
+    assert d["config"]["workload"] == "cfg3_2d_t10x10vp_b512_512x512"
+    assert d["roofline"]["pairs_per_launch"] == 512 * 512 * 512

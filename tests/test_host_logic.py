@@ -171,3 +171,76 @@ def test_theta_sharding_and_gradient_allreduce_world2(tmp_path):
     assert res["ok"]
     assert np.array_equal(res["whole"].numpy(), single)        # sharded == unsharded, bitwise
     assert torch.allclose(res["grad"], torch.full((3,), float(g["theta"].sum())), rtol=1e-5)
+
+
+# ----------------------------------------------------------------- point sharding (configs[3] split)
+class _OracleCpab:
+    """CPU stand-in with the three methods PointShardedCpab calls; backed by the oracle (tests only)."""
+
+    def __init__(self, g):
+        from oracle import oracle as O
+        self.O, self.g, self.nc = O, g, g["nc"].tolist()
+
+    def uniform_meshgrid(self, outsize):
+        return torch.from_numpy(self.O.uniform_meshgrid(outsize))
+
+    def transform_grid(self, grid, theta):
+        As = self.O.theta_to_affine(self.g["B"], theta.numpy(), self.nc)
+        return torch.from_numpy(self.O.forward(grid.numpy(), self.O.affine_to_trels(As), self.nc, 50))
+
+    def interpolate(self, data, grid, outsize):
+        return torch.from_numpy(self.O.interpolate(data.numpy(), grid.numpy(), outsize))
+
+
+def test_point_shard_bounds_are_slabs_of_the_last_dimension():
+    from libcpab_b200.distributed import PointShardedCpab
+    for outsize in ([7], [5, 9], [4, 3, 10]):
+        for ws in (1, 2, 3, 8):
+            spans = [PointShardedCpab(None, r, ws).point_bounds(outsize) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == int(np.prod(outsize))
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            stride = int(np.prod(outsize[:-1]))
+            assert all(lo % stride == 0 and hi % stride == 0 for lo, hi in spans)
+            assert sum(PointShardedCpab(None, r, ws).local_outsize(outsize)[-1] for r in range(ws)) == outsize[-1]
+
+
+def _point_worker(rank, world, port, out):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from libcpab_b200.distributed import PointShardedCpab
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "d2_t3x3.npz"))
+    T = _OracleCpab(g)
+    P = PointShardedCpab(T)
+    outsize = [12, 9]
+    theta = torch.from_numpy(g["theta"])
+    rng = np.random.default_rng(0)
+    data = torch.from_numpy(rng.random((theta.shape[0], 2, 8, 7), dtype=np.float32))
+    local = P.transform_data_local(data, theta, outsize)
+    whole = P.gather_data(local, outsize)
+    # the collective: partial theta-gradients (here: a stand-in that sums the local slab) are summed
+    theta.grad = torch.full_like(theta, float(local.sum()))
+    P.allreduce_theta_grad_(theta)
+    if rank == 0:
+        torch.save({"whole": whole, "grad": theta.grad.clone()}, out)
+    dist.destroy_process_group()
+
+
+def test_point_sharding_world2_gloo(tmp_path):
+    """Two ranks, each a slab of the output grid: gathered slabs == the unsharded result (bitwise),
+    the all-reduce sums the per-slab contributions."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "p0.pt")
+    mp.spawn(_point_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    g = load_golden("d2_t3x3")
+    T = _OracleCpab(g)
+    outsize = [12, 9]
+    theta = torch.from_numpy(g["theta"])
+    rng = np.random.default_rng(0)
+    data = torch.from_numpy(rng.random((theta.shape[0], 2, 8, 7), dtype=np.float32))
+    full = T.interpolate(data, T.transform_grid(T.uniform_meshgrid(outsize), theta), outsize)
+    assert torch.equal(res["whole"], full)
+    assert torch.allclose(res["grad"], torch.full_like(theta, float(full.sum())), rtol=1e-5)
