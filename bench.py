@@ -677,7 +677,14 @@ def reference_cuda_records(ctx, name, ours):
     out_ref = torch.empty(n_theta, ndim, nP, device=ctx.dev)
     ref_fwd = t_ms(lambda: ref_cuda.forward(grid, Tr, tess, 50, out_ref))
     our_fwd = t_ms(lambda: ops.forward(grid, Tr, tess, 50))
-    same = bool((ops.forward(grid, Tr, tess, 50) - out_ref).abs().max().item() < 1e-4)
+    # The reference's CUDA build is FMA-contracted and computes fmod as x - floor(x/y)*y
+    # (cpab_ops.cu:9-12), so it is NOT bit-identical to the reference's CPU extension (which this
+    # library is): a point on or next to a cell face can take the other cell and end elsewhere.
+    # Reported as a distribution, not as a pass/fail.
+    diff = (ops.forward(grid, Tr, tess, 50) - out_ref).abs().amax(dim=1)
+    same = bool(diff.max().item() < 1e-4)
+    frac_same = float((diff < 1e-4).float().mean().item())
+    max_diff = float(diff.max().item())
     # backward: sub-sample so that d * n_s * ndim * nPs * 4 bytes <= 2 GiB
     d = T.params.d
     n_s = min(n_theta, 16)
@@ -700,7 +707,8 @@ def reference_cuda_records(ctx, name, ours):
     return {
         "what": "reference CUDA kernels (libcpab/core/cpab_ops.cu, unmodified, sm_100a) vs this library, same GPU, same inputs",
         "forward": {"pairs": n_theta * nP, "reference_ms": ref_fwd, "ours_ms": our_fwd, "speedup": ref_fwd / our_fwd,
-                    "outputs_agree_1e-4": same},
+                    "outputs_agree_1e-4": same, "fraction_of_points_within_1e-4": frac_same,
+                    "max_abs_diff": max_diff},
         "backward": {"pairs": n_s * nPs, "sample": f"{n_s} thetas x first {nPs} grid points (Jacobian tensor "
                                                      f"{d * n_s * ndim * nPs * 4 / 2**30:.2f} GiB)",
                      "reference_ms": ref_bwd_ms, "ours_ms": our_bwd_ms, "speedup": ref_bwd_ms / our_bwd_ms,
