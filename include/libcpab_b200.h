@@ -126,8 +126,8 @@ int cpab_b200_forward(int dtype, int flags, int ndim, const int* nc, int nsteps,
  * Reference-layout theta-Jacobian.  Replaces cpab_gpu.backward(points, As, Bs, nstepsolver, nc),
  * libcpab/pytorch/transformer_cuda.cpp:43-70 -> transformer_cuda.cu:66-119 -> core/cpab_ops.cu:390-697.
  *   Bs  [d, nC, ndim, ndim+1] (= basis_t)      jac [d, n_theta, ndim, nP]  out
- * Kept for drop-in completeness and op-level parity; it is d-fold redundant by construction and
- * limited to n_theta*d <= 65535.  Training code should use cpab_b200_backward_theta.
+ * Kept for drop-in completeness and op-level parity; it is d-fold redundant by construction.
+ * Training code should use cpab_b200_backward_theta.
  */
 int cpab_b200_backward_jacobian(int dtype, int ndim, const int* nc, int nsteps, int n_theta, int d,
                                 long nP, int broadcast, const void* points, const void* As,

@@ -135,8 +135,9 @@ class Cpab(object):
     def transform_data(self, data, theta, outsize):
         self._check_type(data); self._check_device(data)
         self._check_type(theta); self._check_device(theta)
+        # on theta's own device (one process may drive several GPUs)
         grid = self.backend.uniform_meshgrid(self.params.ndim, self.params.domain_min,
-                                             self.params.domain_max, outsize, self.device, _share=True)
+                                             self.params.domain_max, outsize, theta.device, _share=True)
         if grid.dtype != theta.dtype:
             grid = grid.to(theta.dtype)          # float64 check mode
         p = self.params

@@ -43,6 +43,7 @@ void prof_end(int slot, cudaStream_t st);
 
 int set_tuning(const char* key, int value);
 void set_interp_variant(int v);   // cpab_interp.cu
+void set_interp_max_ctas(int v);
 const char* get_error();
 
 #define CPAB_CUDA_OK(expr)                                                                   \

@@ -211,15 +211,16 @@ k_jacobian(const T* __restrict__ points, const T* __restrict__ As, const T* __re
            T* __restrict__ jac, long nP, int n_theta, int d, int broadcast, int nsteps, const __grid_constant__ Geom g)
 {
     constexpr int PPC = Dim<NDIM>::kPpc;
-    const int tk = blockIdx.y;                      // theta * d + k  (host keeps n_theta*d <= 65535,
-    const int theta = tk / d, k = tk - theta * d;   //  otherwise loops over slabs)
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nP) return;
     const size_t tsize = (size_t)g.n_cells * PPC;
+    const double h = 1.0 / nsteps;
+    // blockIdx.y walks over (theta, k) pairs; more than 65535 of them are taken in strides
+    for (long tk = blockIdx.y; tk < (long)n_theta * d; tk += gridDim.y) {
+    const int theta = (int)(tk / d), k = (int)(tk - (long)theta * d);
     const T* At = As + (size_t)theta * tsize;
     const T* Bk = Bs + (size_t)k * tsize;
     const T* src = points + (broadcast ? (size_t)theta * NDIM * nP : 0);
-    const double h = 1.0 / nsteps;
 
     T p[NDIM], q[NDIM];
 #pragma unroll
@@ -254,6 +255,7 @@ k_jacobian(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     T* dst = jac + ((size_t)k * n_theta + theta) * NDIM * nP;
 #pragma unroll
     for (int j = 0; j < NDIM; ++j) dst[i + (long)j * nP] = q[j];
+    }
 }
 
 // dtheta[t][k] = sum_e G[t][e] * B[e][k]      (G [n_theta,D], B [D,d] row-major, dtheta [n_theta,d])
@@ -326,7 +328,8 @@ int set_tuning(const char* key, int value)
     if (k == "bwd_seg" && (value == 0 || value == 3 || value == 5 || value == 10)) { t.bwd_seg = value; return kOk; }
     if (k == "bwd_stage" && value >= -1 && value <= 1) { t.bwd_stage = value; return kOk; }
     if (k == "bwd_block" && (value == 64 || value == 128 || value == 256)) { t.bwd_block = value; return kOk; }
-    if (k == "interp_variant" && value >= 0 && value <= 4) { set_interp_variant(value); return kOk; }
+    if (k == "interp_variant" && value >= 0 && value <= 8) { set_interp_variant(value); return kOk; }
+    if (k == "interp_max_ctas" && value >= 0) { set_interp_max_ctas(value); return kOk; }
     set_error("unknown tuning key/value %s=%d", key, value);
     return kErrArgument;
 }
@@ -462,8 +465,7 @@ static int jacobian_t(const Geom& g, int nsteps, int n_theta, int d, long nP, in
                       const void* points, const void* As, const void* Bs, void* jac, cudaStream_t st)
 {
     const long long tk = (long long)n_theta * d;
-    if (tk > 65535) { set_error("jacobian: n_theta*d = %lld exceeds 65535 (use backward_theta)", tk); return kErrUnsupported; }
-    dim3 grid((unsigned)((nP + 127) / 128), (unsigned)tk);
+    dim3 grid((unsigned)((nP + 127) / 128), (unsigned)(tk < 65535 ? tk : 65535));
     k_jacobian<T, NDIM><<<grid, 128, 0, st>>>((const T*)points, (const T*)As, (const T*)Bs, (T*)jac,
                                                nP, n_theta, d, broadcast, nsteps, g);
     count_launch();
@@ -589,6 +591,8 @@ static bool make_sample_shape(int ndim, int N, int C, const int* in_size, const 
         if (j < ndim) { gridpts *= out_size[j]; inpts *= in_size[j]; }
     }
     nP = (long)gridpts;
+    for (int j = 0; j < ndim; ++j)
+        if (in_size[j] > kMaxInterpExtentF32) { set_error("transform_data: input extent %d exceeds %d", in_size[j], kMaxInterpExtentF32); return false; }
     if (gridpts * ndim >= (1LL << 31) || inpts >= (1LL << 31) || gridpts * C >= (1LL << 31)) {
         set_error("transform_data: one sample exceeds 2^31 elements");
         return false;

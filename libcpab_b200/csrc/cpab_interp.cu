@@ -24,7 +24,8 @@ namespace cpab {
 
 namespace {
 
-int g_interp_variant = 2;   // 0: 4 points in flight, 1 CTA/SM target; 1: 2 / 6; 2: 1 / 8 (default, measured best) (cpab_b200_set_tuning "interp_variant")
+int g_interp_max_ctas = 0;  // tests: cap the persistent grid so that every CTA walks over many tiles ("interp_max_ctas")
+int g_interp_variant = 5;   // 0-4: one tile per CTA (0: 4 points in flight, 1 CTA/SM target; 1: 2 / 6; 2: 1 / 8); 5-8: persistent pipelined kernels (float32; default 5) (cpab_b200_set_tuning "interp_variant")
 
 // ---------------------------------------------------------------------------------------------
 // forward.  NDIM >= 2: CTA = 256 threads, tile 32 (first index) x 32 (last index);
@@ -268,6 +269,342 @@ k_interp_bwd(const T* __restrict__ data, const T* __restrict__ grid, const T* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent, software-pipelined variants (float32, NDIM >= 2, first output extent a multiple of 4)
+// -- the default.
+//
+// The one-tile-per-CTA kernels above pay two dependent HBM round trips per tile (grid tile, then
+// texels), one CTA launch per 1024 points and ~24 instructions per point for the staging alone.
+// Here a CTA walks over tiles (grid = resident CTAs only) and keeps the grid tiles of the next two
+// iterations in flight with 16-byte cp.async (LDGSTS: global -> shared without passing through
+// registers) in a 3-stage ring: a tile's coordinates are already in shared memory when its turn
+// comes and the only exposed latency per tile is the texel gather, which all four points of a
+// thread issue together.  One __syncthreads per tile: it publishes the landed stage and, at the
+// same time, retires the stage that is about to be refilled (read during the previous iteration).
+//
+// Stage layout: [NDIM][TILE rows (last output index)][PITCH = 36 floats].  Copy mapping: thread t
+// moves the 16-byte chunk (row t/8, chunk t%8) of every coordinate plane -- 8 threads cover 128
+// contiguous bytes of global memory.  Compute mapping: lane = row (runs along the last output index:
+// texel gathers and stores are unit-stride for near-identity warps), warp w owns the FOUR first-index
+// points 4w..4w+3 of its row and reads their coordinates with ONE LDS.128 per plane; with the
+// 144-byte pitch the eight lanes of a quarter-warp hit disjoint bank groups (conflict-free).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStages = 3;
+constexpr int PITCH = TILE + 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// shared memory through 32-bit window addresses (a generic pointer into the ring makes ptxas rebuild
+// the window base -- S2UR SR_CgaCtaId, ULEA -- in every iteration)
+__device__ __forceinline__ void lds_f32x4(uint32_t a, float* v)
+{
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_f32x4(uint32_t a, const float* v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
+// Tiles are numbered first-index-fastest: t = ((n * mid + im) * tiles_f + tf) * tiles_a + ta.  A CTA
+// visits t = blockIdx.x + k * gridDim.x; the position is kept as mixed-radix digits and advanced by
+// the digits of gridDim.x (host-computed) with carries -- no division in the tile loop.
+struct TileGeom {
+    int tiles_a, tiles_f, mid;      // tiles along the first / last output index, middle extent (3-D)
+    int da, df, dm, dn;             // gridDim.x in the same radix
+};
+
+struct TilePos { int n, im, a0, f0; };
+
+struct TileCursor {
+    int ta, tf, im, n;
+    __device__ __forceinline__ void init(unsigned t, const TileGeom& tg)
+    {
+        unsigned q = t / (unsigned)tg.tiles_a;
+        ta = (int)(t - q * tg.tiles_a);
+        unsigned q2 = q / (unsigned)tg.tiles_f;
+        tf = (int)(q - q2 * tg.tiles_f);
+        n = (int)(q2 / (unsigned)tg.mid);
+        im = (int)(q2 - (unsigned)n * tg.mid);
+    }
+    __device__ __forceinline__ void advance(const TileGeom& tg)
+    {
+        ta += tg.da;
+        tf += tg.df;
+        if (ta >= tg.tiles_a) { ta -= tg.tiles_a; ++tf; }
+        im += tg.dm;
+        if (tf >= tg.tiles_f) { tf -= tg.tiles_f; ++im; }
+        n += tg.dn;
+        if (im >= tg.mid) { im -= tg.mid; ++n; }
+    }
+    __device__ __forceinline__ TilePos pos() const { return TilePos{n, im, ta * TILE, tf * TILE}; }
+};
+
+// element offset (within one coordinate plane of sample n) of this thread's 16-byte chunk of the
+// tile at `tp`.  Rows / chunks beyond the image are clamped to its last row / chunk: those entries
+// hold valid but unused values, and no copy needs a predicate.
+template <int NDIM>
+__device__ __forceinline__ size_t chunk_offset(const Shape& s, const TilePos& tp)
+{
+    const int row = threadIdx.x >> 3, ch = threadIdx.x & 7;
+    const int O0 = s.O[0];
+    const unsigned pstride = (unsigned)(NDIM == 2 ? O0 : O0 * s.O[1]);
+    const unsigned nP = pstride * (unsigned)s.O[NDIM - 1];
+    const int ix = min(tp.a0 + 4 * ch, O0 - 4);
+    const unsigned f = (unsigned)min(tp.f0 + row, s.O[NDIM - 1] - 1);
+    return (size_t)tp.n * NDIM * nP + (size_t)pstride * f + (size_t)((NDIM == 3 ? O0 * tp.im : 0) + ix);
+}
+
+template <int NDIM>
+__device__ __forceinline__ void prefetch_grid_tile(const float* __restrict__ grid, const Shape& s,
+                                                   const TileCursor& cur, uint32_t sg)
+{
+    if (cur.n < s.N) {
+        const unsigned nP = (unsigned)(s.O[0] * s.O[1] * (NDIM >= 3 ? s.O[2] : 1));
+        const float* src = grid + chunk_offset<NDIM>(s, cur.pos());
+        const uint32_t dst = sg + 4u * (uint32_t)((threadIdx.x >> 3) * PITCH + 4 * (threadIdx.x & 7));
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) cp_async16(dst + 4u * (uint32_t)(j * TILE * PITCH), src + (size_t)j * nP);
+    }
+    cp_async_commit();      // (an empty group when there is no tile: keeps the group count uniform)
+}
+
+template <int NDIM, bool FULL, bool ONECH>
+__device__ __forceinline__ void interp_fwd_compute(const float* __restrict__ data, float* __restrict__ out, const Shape& s,
+                                                   const TilePos& tp, uint32_t sg)
+{
+    constexpr int NC = 1 << NDIM;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int O0 = s.O[0], OF = s.O[NDIM - 1];
+    const int nP = O0 * s.O[1] * (NDIM >= 3 ? s.O[2] : 1);
+    const int iF = tp.f0 + lane, iA = tp.a0 + 4 * wrp;
+    const int plane = s.S[0] * s.S[1] * (NDIM >= 3 ? s.S[2] : 1);
+    const float* dn = data + (size_t)tp.n * s.C * plane;
+    asm volatile("" : "+l"(dn));       // one base pointer per image: every gather address is then one IMAD.WIDE
+    const int ostride = NDIM == 2 ? s.O[1] : s.O[1] * s.O[2];            // output stride of the first index
+    float* on = out + (size_t)tp.n * s.C * nP + (NDIM == 2 ? iA * s.O[1] + iF : (iA * s.O[1] + tp.im) * s.O[2] + iF);
+    const int nch = ONECH ? 1 : s.C;
+    float gc[NDIM][4];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) lds_f32x4(sg + 4u * (uint32_t)((j * TILE + lane) * PITCH + 4 * wrp), gc[j]);
+    Taps<float, NDIM> tq[4];
+    bool ok[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        ok[b] = FULL || (iA + b < O0 && iF < OF);
+        float g1[NDIM];
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) g1[j] = gc[j][b];
+        tq[b] = make_taps<float, NDIM>(g1, s);
+    }
+    const float* dp = dn;
+    float* op = on;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c, dp += plane, op += nP) {
+        float v[4][NC];
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (FULL || ok[b]) gather<float, NDIM>(dp, tq[b], v[b]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (FULL || ok[b]) op[b * ostride] = blend<NDIM>(v[b], tq[b].w);
+    }
+}
+
+template <int NDIM, int MINB, bool ONECH>
+__global__ void __launch_bounds__(256, MINB)
+k_interp_fwd_pipe(const float* __restrict__ data, const float* __restrict__ grid, float* __restrict__ out,
+                  const __grid_constant__ Shape s, const __grid_constant__ TileGeom tg)
+{
+    extern __shared__ __align__(16) float sg_ring[];       // [kStages][NDIM][TILE][PITCH]
+    constexpr int STAGE = NDIM * TILE * PITCH;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sg_ring);
+    TileCursor cur, pf;                 // tile being computed / tile being prefetched (two ahead)
+    cur.init(blockIdx.x, tg);
+    pf = cur;
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring);
+    pf.advance(tg);
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * STAGE);
+    int stage = 0;
+    for (; cur.n < s.N; cur.advance(tg)) {
+        cp_async_wait<1>();
+        __syncthreads();
+        const int nxt = stage >= 1 ? stage - 1 : kStages - 1;      // (stage + 2) % 3
+        pf.advance(tg);
+        prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * (uint32_t)(nxt * STAGE));
+        const TilePos tp = cur.pos();
+        const bool full = (tp.a0 + TILE <= s.O[0]) && (tp.f0 + TILE <= s.O[NDIM - 1]);
+        const uint32_t sg = ring + 4u * (uint32_t)(stage * STAGE);
+        if (full) interp_fwd_compute<NDIM, true, ONECH>(data, out, s, tp, sg);
+        else interp_fwd_compute<NDIM, false, ONECH>(data, out, s, tp, sg);
+        stage = stage + 1 == kStages ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+}
+
+// backward: d/dgrid goes back through the tile's own stage (every thread overwrites exactly the
+// entries it read) and leaves in the copy mapping, 16 bytes per thread and plane.
+template <int NDIM, bool FULL, bool DDATA, int BATCH>
+__device__ __forceinline__ void interp_bwd_compute(const float* __restrict__ data, const float* __restrict__ gout,
+                                                   float* __restrict__ dgrid, float* __restrict__ ddata,
+                                                   const Shape& s, const TilePos& tp, uint32_t sg)
+{
+    constexpr int NC = 1 << NDIM;
+    constexpr int H = 1 << (NDIM - 1);
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int O0 = s.O[0], OF = s.O[NDIM - 1];
+    const int nP = O0 * s.O[1] * (NDIM >= 3 ? s.O[2] : 1);
+    const int iF = tp.f0 + lane, iA = tp.a0 + 4 * wrp;
+    const int plane = s.S[0] * s.S[1] * (NDIM >= 3 ? s.S[2] : 1);
+    const float* dn = data + (size_t)tp.n * s.C * plane;
+    asm volatile("" : "+l"(dn));
+    float* ddn = DDATA ? ddata + (size_t)tp.n * s.C * plane : nullptr;
+    const int ostride = NDIM == 2 ? s.O[1] : s.O[1] * s.O[2];
+    const float* gon = gout + (size_t)tp.n * s.C * nP + (NDIM == 2 ? iA * s.O[1] + iF : (iA * s.O[1] + tp.im) * s.O[2] + iF);
+    const int nch = s.C;
+    const uint32_t mine = sg + 4u * (uint32_t)(lane * PITCH + 4 * wrp);
+    float gc[NDIM][4], dg[NDIM][4];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) lds_f32x4(mine + 4u * (uint32_t)(j * TILE * PITCH), gc[j]);
+#pragma unroll
+    for (int r0 = 0; r0 < 4; r0 += BATCH) {
+        Taps<float, NDIM> tq[BATCH];
+        bool ok[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            ok[b] = FULL || (iA + r0 + b < O0 && iF < OF);
+            float g1[NDIM];
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) { g1[j] = gc[j][r0 + b]; dg[j][r0 + b] = 0; }
+            tq[b] = make_taps<float, NDIM>(g1, s);
+        }
+        const float* dp = dn;
+        const float* gp = gon + r0 * ostride;
+        float* qd = ddn;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c, dp += plane, gp += nP) {
+            float v[BATCH][NC], g[BATCH];
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                if (FULL || ok[b]) {
+                    gather<float, NDIM>(dp, tq[b], v[b]);
+                    g[b] = __ldg(gp + b * ostride);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                if (FULL || ok[b]) {
+                    float gv[NC], dw[NDIM];
+                    blend_vjp<NDIM>(v[b], tq[b].w, g[b], gv, dw);
+#pragma unroll
+                    for (int j = 0; j < NDIM; ++j) dg[j][r0 + b] += dw[j];
+                    if (DDATA) {
+#pragma unroll
+                        for (int u = 0; u < H; ++u) {
+                            atomicAdd(qd + tq[b].base[u], gv[u]);
+                            atomicAdd(qd + tq[b].base[u] + (tq[b].two ? 1 : 0), gv[u + H]);
+                        }
+                    }
+                }
+            }
+            if (DDATA) qd += plane;
+        }
+    }
+    if (dgrid == nullptr) return;
+    // xd = x - x0 with x = g*(size-1): d/dg = size-1
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) {
+        const float sc = (float)(s.S[j] - 1);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dg[j][b] *= sc;
+        sts_f32x4(mine + 4u * (uint32_t)(j * TILE * PITCH), dg[j]);
+    }
+    __syncthreads();
+    const int row = threadIdx.x >> 3, ch = threadIdx.x & 7;
+    if (FULL || (tp.a0 + 4 * ch < O0 && tp.f0 + row < OF)) {
+        float* dst = dgrid + chunk_offset<NDIM>(s, tp);
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            float v[4];
+            lds_f32x4(sg + 4u * (uint32_t)((j * TILE + row) * PITCH + 4 * ch), v);
+            *reinterpret_cast<float4*>(dst + (size_t)j * nP) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+template <int NDIM, int BATCH, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_interp_bwd_pipe(const float* __restrict__ data, const float* __restrict__ grid, const float* __restrict__ gout,
+                  float* __restrict__ dgrid, float* __restrict__ ddata, const __grid_constant__ Shape s,
+                  const __grid_constant__ TileGeom tg)
+{
+    extern __shared__ __align__(16) float sg_ring[];
+    constexpr int STAGE = NDIM * TILE * PITCH;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sg_ring);
+    TileCursor cur, pf;
+    cur.init(blockIdx.x, tg);
+    pf = cur;
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring);
+    pf.advance(tg);
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * STAGE);
+    int stage = 0;
+    for (; cur.n < s.N; cur.advance(tg)) {
+        cp_async_wait<1>();
+        __syncthreads();
+        const int nxt = stage >= 1 ? stage - 1 : kStages - 1;
+        pf.advance(tg);
+        prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * (uint32_t)(nxt * STAGE));
+        const TilePos tp = cur.pos();
+        const bool full = (tp.a0 + TILE <= s.O[0]) && (tp.f0 + TILE <= s.O[NDIM - 1]);
+        const uint32_t sg = ring + 4u * (uint32_t)(stage * STAGE);
+        if (ddata != nullptr) {
+            if (full) interp_bwd_compute<NDIM, true, true, BATCH>(data, gout, dgrid, ddata, s, tp, sg);
+            else interp_bwd_compute<NDIM, false, true, BATCH>(data, gout, dgrid, ddata, s, tp, sg);
+        } else {
+            if (full) interp_bwd_compute<NDIM, true, false, BATCH>(data, gout, dgrid, ddata, s, tp, sg);
+            else interp_bwd_compute<NDIM, false, false, BATCH>(data, gout, dgrid, ddata, s, tp, sg);
+        }
+        stage = stage + 1 == kStages ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+}
+
+template <typename KERN, typename... Args>
+static int launch_pipe(KERN kern, int ndim, const Shape& s, cudaStream_t st, int slot, Args... args)
+{
+    TileGeom tg;
+    tg.tiles_a = (s.O[0] + TILE - 1) / TILE;
+    tg.tiles_f = (s.O[ndim - 1] + TILE - 1) / TILE;
+    tg.mid = ndim == 3 ? s.O[1] : 1;
+    const long long total = (long long)s.N * tg.mid * tg.tiles_f * tg.tiles_a;
+    if (total >= (1LL << 31)) { set_error("interpolate: %lld tiles exceed 2^31", total); return kErrUnsupported; }
+    const size_t smem = (size_t)kStages * ndim * TILE * PITCH * sizeof(float);
+    if (smem > 48 * 1024) CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, dev = 0, sms = 0;
+    CPAB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    CPAB_CUDA_OK(cudaGetDevice(&dev));
+    CPAB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long blocks = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    if (g_interp_max_ctas > 0 && blocks > g_interp_max_ctas) blocks = g_interp_max_ctas;
+    if (blocks > total) blocks = total;
+    {   // gridDim.x in the radix (tiles_a, tiles_f, mid)
+        long long q = blocks;
+        tg.da = (int)(q % tg.tiles_a); q /= tg.tiles_a;
+        tg.df = (int)(q % tg.tiles_f); q /= tg.tiles_f;
+        tg.dm = (int)(q % tg.mid);     q /= tg.mid;
+        tg.dn = (int)q;
+    }
+    prof_begin(slot, st);
+    kern<<<(unsigned)blocks, 256, smem, st>>>(args..., s, tg);
+    prof_end(slot, st);
+    count_launch();
+    CPAB_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_interp_bwd_1d(const T* __restrict__ data, const T* __restrict__ grid, const T* __restrict__ gout,
@@ -318,6 +655,10 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
 {
     if (s.N == 0 || s.C == 0) return kOk;
     for (int j = 0; j < ndim; ++j) if (s.O[j] == 0) return kOk;
+    if (sizeof(T) == 4) {
+        for (int j = 0; j < ndim; ++j)
+            if (s.S[j] > kMaxInterpExtentF32) { set_error("interpolate: float32 input extent %d exceeds %d", s.S[j], kMaxInterpExtentF32); return kErrUnsupported; }
+    }
     if (ndim == 1) {
         dim3 g((unsigned)((s.O[0] + 256 * PT1D - 1) / (256 * PT1D)), (unsigned)s.N);
         if (s.N > 65535) {   // grid.y limit: slab the batch
@@ -348,6 +689,29 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
         if (gridpts * ndim >= (1LL << 31) || inpts >= (1LL << 31) || gridpts * s.C >= (1LL << 31)) {
             set_error("interpolate: one sample exceeds 2^31 elements");
             return kErrUnsupported;
+        }
+    }
+    if constexpr (sizeof(T) == 4) {
+        // persistent, pipelined kernels (variants 5-8: resident CTAs targeted / points whose gathers
+        // are in flight together in the backward); they move 16-byte chunks of the grid, which
+        // needs 16-byte aligned planes -- anything else takes the one-tile-per-CTA kernels
+        const int var = g_interp_variant;
+        const float* d = (const float*)data; const float* gr = (const float*)grid; const float* go = (const float*)gout;
+        float* o = (float*)out_or_dgrid; float* dd = (float*)ddata;
+        const bool aligned = s.O[0] % 4 == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0 &&
+                             (!backward || out_or_dgrid == nullptr || (reinterpret_cast<uintptr_t>(out_or_dgrid) & 15) == 0);
+        if (var >= 5 && aligned) {
+#define FWD(ND, M) (s.C == 1 ? launch_pipe(k_interp_fwd_pipe<ND, M, true>, ndim, s, st, kProfInterpFwd, d, gr, o) \
+                             : launch_pipe(k_interp_fwd_pipe<ND, M, false>, ndim, s, st, kProfInterpFwd, d, gr, o))
+#define BWD(ND, B, M) launch_pipe(k_interp_bwd_pipe<ND, B, M>, ndim, s, st, kProfInterpBwd, d, gr, go, o, dd)
+            if (ndim == 2) {
+                if (!backward) return var == 5 ? FWD(2, 4) : var == 6 ? FWD(2, 5) : var == 7 ? FWD(2, 6) : FWD(2, 3);
+                return var == 5 ? BWD(2, 2, 4) : var == 6 ? BWD(2, 4, 3) : var == 7 ? BWD(2, 1, 5) : BWD(2, 4, 2);
+            }
+            if (!backward) return var == 5 ? FWD(3, 3) : var == 6 ? FWD(3, 4) : var == 7 ? FWD(3, 2) : FWD(3, 5);
+            return var == 5 ? BWD(3, 1, 3) : var == 6 ? BWD(3, 2, 2) : var == 7 ? BWD(3, 1, 4) : BWD(3, 4, 1);
+#undef FWD
+#undef BWD
         }
     }
     const long z = (long)s.N * (ndim == 3 ? s.O[1] : 1);
@@ -395,6 +759,7 @@ Shape make_shape(int ndim, int N, int C, const int* in_size, const int* out_size
 }  // namespace
 
 void set_interp_variant(int v) { g_interp_variant = v; }
+void set_interp_max_ctas(int v) { g_interp_max_ctas = v; }
 
 int launch_interp_forward(int dtype, int ndim, int N, int C, const int* in_size, const int* out_size,
                           const void* data, const void* grid, void* out, cudaStream_t st)

@@ -43,6 +43,29 @@ __device__ __forceinline__ void taps(T gcoord, int size, int& t0, int& t1, T& wg
     wgt = R<T>::sub(x, f0);
 }
 
+// float32: the same values without a conversion-pipe instruction (FRND + 2 F2I per coordinate run
+// at 16 lanes/clk/SM on a B200, profiles/r02_pipe_probe.txt).  For x in [-1, 2^22) the sum
+// x + 1.5*2^23 rounded DOWN is exactly 1.5*2^23 + floor(x) (ulp 1 in [2^23, 2^24)), so the integer
+// floor is a difference of bit patterns; x below -1 (and NaN: fmaxf returns the other operand) is
+// lifted to -1, which has the same clamped taps (0, 0); x >= 2^22 yields an integer >= 2^22 > size-1,
+// clamped to size-1 like the reference's floor.  The clamped lower tap goes back to float through
+// the same constant (exact), and the weight is formed from the unclamped x as the reference does.
+// Requires size <= 2^22 (kMaxInterpExtentF32; the launchers refuse larger float32 extents).
+// `t1 - t0` is 0 or 1.
+template <>
+__device__ __forceinline__ void taps<float>(float gcoord, int size, int& t0, int& t1, float& wgt)
+{
+    const int ihi = size - 1;
+    const float hi = (float)ihi;
+    const float x = __fmul_rn(gcoord, hi);
+    const float magic = 12582912.0f;                        // 1.5 * 2^23 = 0x4B400000
+    const float t = __fadd_rd(fmaxf(x, -1.0f), magic);
+    const int i = __float_as_int(t) - 0x4B400000;           // floor(x), any int when |x| is huge
+    t0 = min(max(i, 0), ihi);
+    t1 = t0 + ((unsigned)i < (unsigned)ihi ? 1 : 0);        // clamp(i + 1) differs from t0 iff 0 <= i < size-1
+    wgt = __fsub_rn(x, __fsub_rn(__int_as_float(t0 + 0x4B400000), magic));
+}
+
 // multilinear blend of 2^NDIM corner values, x first (bit 0), then y, then z
 template <int NDIM, typename T>
 __device__ __forceinline__ T blend(const T* v, const T* w)
@@ -91,6 +114,7 @@ __device__ __forceinline__ void blend_vjp(const T* v, const T* w, T g, T* gv, T*
     for (int i = 0; i < (1 << NDIM); ++i) gv[i] = gl[i];
 }
 
+constexpr int kMaxInterpExtentF32 = 1 << 22;
 constexpr int TILE = 32;
 constexpr int REPS = TILE / 8;
 
@@ -112,18 +136,20 @@ __device__ __forceinline__ Taps<T, NDIM> make_taps(const T* gcoord, const Shape&
 #pragma unroll
     for (int j = 0; j < NDIM; ++j) taps(gcoord[j], s.S[j], t0[j], t1[j], tp.w[j]);
     tp.two = t1[NDIM - 1] != t0[NDIM - 1];
+    // t1 - t0 is 0 or 1 per dimension: neighbouring rows / slabs are an optional stride away
     if (NDIM == 1) {
         tp.base[0] = t0[0];
     } else if (NDIM == 2) {
         tp.base[0] = t0[0] * s.S[1] + t0[1];
-        tp.base[1] = t1[0] * s.S[1] + t0[1];
+        tp.base[1] = tp.base[0] + (t1[0] != t0[0] ? s.S[1] : 0);
     } else {
-        const int r00 = t0[0] * s.S[1] + t0[1], r10 = t1[0] * s.S[1] + t0[1];
-        const int dy = t1[1] - t0[1];
-        tp.base[0] = r00 * s.S[2] + t0[2];
-        tp.base[1] = r10 * s.S[2] + t0[2];
-        tp.base[2] = (r00 + dy) * s.S[2] + t0[2];
-        tp.base[3] = (r10 + dy) * s.S[2] + t0[2];
+        const int r = (t0[0] * s.S[1] + t0[1]) * s.S[2] + t0[2];
+        const int sx = t1[0] != t0[0] ? s.S[1] * s.S[2] : 0;
+        const int sy = t1[1] != t0[1] ? s.S[2] : 0;
+        tp.base[0] = r;
+        tp.base[1] = r + sx;
+        tp.base[2] = r + sy;
+        tp.base[3] = r + sx + sy;
     }
     return tp;
 }

@@ -17,11 +17,16 @@ def assert_version():
 
 
 def _device(device):
-    if isinstance(device, torch.device):
-        return device
+    """'gpu' means the CURRENT CUDA device, resolved to a concrete index (the reference creates its
+    tensors on the current device at every call; a bare torch.device('cuda') used as a cache key
+    would pin whatever device was current at first use)."""
     if device is None:
         return None
-    return torch.device("cuda") if device in ("gpu", "cuda") else torch.device(device)
+    if not isinstance(device, torch.device):
+        device = torch.device("cuda") if device in ("gpu", "cuda") else torch.device(device)
+    if device.type == "cuda" and device.index is None and torch.cuda.is_available():
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
 
 
 def to(x, dtype=torch.float32, device=None):

@@ -32,7 +32,12 @@ def pytest_collection_modifyitems(config, items):
 def golden_cases():
     """Names of the op/API-level fixtures generated from the reference (make_golden.py)."""
     names = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if n not in ("cells", "expm", "seq_1d20x3")]
+    return [n for n in names if n not in ("cells", "expm", "seq_1d20x3") and not n.startswith("aux_")]
+
+
+def aux_cases():
+    """Fixtures of calc_vectorfield and the smooth prior's covariance (make_golden_aux.py)."""
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "aux_*.npz")))
 
 
 def load_golden(name):

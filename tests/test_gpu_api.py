@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import flow_gain, golden_cases, load_golden, rel_err
+from conftest import aux_cases, flow_gain, golden_cases, load_golden, rel_err
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -222,3 +222,30 @@ def test_fused_transform_data_multichannel_and_fp64():
                 grads.append((out.detach(), th.grad))
             assert torch.equal(grads[0][0], grads[1][0])
             assert rel_err(grads[0][1].cpu().numpy(), grads[1][1].cpu().numpy()) < (2e-6 if dt == torch.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("name", aux_cases())
+def test_calc_vectorfield_and_prior_match_reference(name):
+    """`Cpab.calc_vectorfield` (libcpab/pytorch/functions.py:111-129) and the theta-space covariance
+    `sample_transformation_with_prior` builds (libcpab/cpab.py:211-237) against fixtures made by the
+    reference itself (tests/golden/make_golden_aux.py)."""
+    g = load_golden(name)
+    T = make_T(g)
+    v = T.calc_vectorfield(cuda(g["grid"]), cuda(g["theta"]))
+    assert tuple(v.shape) == g["vectorfield"].shape
+    e_v = rel_err(v.cpu().numpy(), g["vectorfield"])
+    seen = {}
+    real = T.sample_transformation
+
+    def spy(n_sample=1, mean=None, cov=None):
+        seen["cov"] = cov
+        return real(n_sample, mean=mean, cov=cov)
+
+    T.sample_transformation = spy
+    s = T.sample_transformation_with_prior(5, length_scale=float(g["length_scale"]),
+                                           output_variance=float(g["output_variance"]))
+    assert tuple(s.shape) == (5, T.params.d) and s.is_cuda and bool(torch.isfinite(s).all())
+    e_c = rel_err(seen["cov"].cpu().numpy(), g["cov_theta"])
+    print("%s: vectorfield rel err %.3g, prior covariance rel err %.3g" % (name, e_v, e_c))
+    assert e_v < 2e-5      # zero-boundary fields cancel (|a x|, |b| >> |a x + b|): float32 evaluation order
+    assert e_c < 1e-5

@@ -380,6 +380,55 @@ def test_interpolate_ragged_shapes_and_outside_points(shape, outsize):
     assert rel_err(out64.cpu().numpy(), O.interpolate(data.astype(np.float64), grid.astype(np.float64), outsize)) < 1e-14
 
 
+@pytest.mark.parametrize("shape,outsize,cap", [((5, 1, 40, 33), (70, 100), 3), ((3, 2, 21, 30), (65, 129), 7),
+                                               ((2, 1, 9, 11, 13), (40, 6, 70), 2), ((1, 2, 12, 7, 9), (33, 3, 33), 0)])
+def test_interpolate_persistent_kernels_walk_many_tiles(shape, outsize, cap):
+    """The float32 interpolate kernels are persistent (a CTA walks over 32x32 tiles with the grid
+    tiles of the next two iterations in flight).  With the grid capped to a few CTAs every CTA
+    goes around its 3-stage ring several times, over interior and ragged edge tiles alike."""
+    from libcpab_b200 import _lib, ops
+    rng = np.random.default_rng(sum(shape) + cap)
+    ndim = len(shape) - 2
+    data = rng.uniform(size=shape).astype(np.float32)
+    grid = rng.uniform(-0.2, 1.2, (shape[0], ndim, int(np.prod(outsize)))).astype(np.float32)
+    gout = rng.normal(size=(shape[0], shape[1], *outsize)).astype(np.float32)
+    ref = O.interpolate(data, grid, outsize)
+    dg_o, dd_o = O.interpolate_vjp(data, grid, outsize, gout)
+    try:
+        _lib.set_tuning("interp_max_ctas", cap)
+        for var in (5, 6, 7, 8):
+            _lib.set_tuning("interp_variant", var)
+            out = ops.interpolate_forward(dev(data), dev(grid), outsize).cpu().numpy()
+            assert np.array_equal(out, ref), var
+            dgrid, ddata = ops.interpolate_backward(dev(data), dev(grid), dev(gout), True, True)
+            assert rel_err(dgrid.cpu().numpy(), dg_o) < F32_TOL, var
+            assert rel_err(ddata.cpu().numpy(), dd_o) < F32_TOL, var
+            dgrid2, none = ops.interpolate_backward(dev(data), dev(grid), dev(gout), True, False)
+            assert none is None and torch.equal(dgrid2, dgrid), var
+    finally:
+        _lib.set_tuning("interp_max_ctas", 0)
+        _lib.set_tuning("interp_variant", 5)
+
+
+def test_interpolate_taps_extreme_coordinates():
+    """The conversion-free tap arithmetic (cpab_sample.cuh) against the oracle on coordinates far
+    outside the image, exactly on texels, just below them, negative zero, and huge (below 2^63 after
+    scaling: beyond, the reference's float -> int64 conversion is itself undefined)."""
+    from libcpab_b200 import ops
+    W, H = 17, 9
+    rng = np.random.default_rng(3)
+    data = rng.uniform(size=(1, 1, W, H)).astype(np.float32)
+    xs = np.array([0.0, -0.0, 1.0, np.nextafter(np.float32(1), np.float32(0)), np.nextafter(np.float32(1), np.float32(2)),
+                   -1e-8, 1e-8, 0.5, 1.0 / 16, 3.0 / 16 - 1e-7, -0.07, -1.0, -3.5, 2.0, 7.25, 1e6, -1e6, 3e9, -3e9],
+                  dtype=np.float32)
+    gx, gy = np.meshgrid(xs, xs, indexing="ij")
+    n = xs.size
+    grid = np.stack([gx.ravel(), gy.ravel()])[None].astype(np.float32)
+    out = ops.interpolate_forward(dev(data), dev(grid), [n, n]).cpu().numpy()
+    ref = O.interpolate(data, grid, [n, n])
+    assert np.array_equal(out, ref, equal_nan=True)
+
+
 # ------------------------------------------------------------------------------------- error path
 def test_errors_are_raised_not_swallowed():
     from libcpab_b200 import _lib, ops

@@ -138,3 +138,38 @@ def test_reference_gradient_moves_more_than_1e5_between_float32_and_float64():
     errs = theta_errs(g32, g64)
     assert errs.max() > 2e-5, errs.max()
     assert np.median(errs) < 5e-6, np.median(errs)
+
+
+# ------------------------------------------------------------------ prior covariance / vector field
+def _prior_cov(B, centers, ppc, length_scale, output_variance):
+    """libcpab/cpab.py:211-237 restated: squared-exponential kernel on squared centre distances on
+    the per-parameter diagonal of every (cell, cell) block, 100 * max distance elsewhere."""
+    c = np.asarray(centers, dtype=np.float64)
+    n2 = (c * c).sum(1)[:, None]
+    dist = n2 - 2 * c @ c.T + n2.T
+    eye = np.eye(ppc)
+    cov_init = np.kron(dist, eye) + np.kron(np.ones_like(dist), 100 * dist.max() * (1 - eye))
+    cov_avees = output_variance ** 2 * np.exp(-(cov_init / (2 * length_scale ** 2)))
+    return B.T @ cov_avees @ B
+
+
+@pytest.mark.parametrize("name", __import__("conftest").aux_cases())
+def test_prior_covariance_and_vectorfield_restatements_match_reference(name):
+    """The reference's smooth prior (its block loop, run by make_golden_aux.py) equals the Kronecker
+    restatement the product uses; its calc_vectorfield equals A[cell(p)] [p;1] with the oracle's cells;
+    the product's cell centres are the reference's."""
+    from libcpab_b200.tessellation import cell_vertices
+    g = load_golden(name)
+    nc = g["nc"].tolist()
+    ndim = len(nc)
+    ppc = ndim * (ndim + 1)
+    cov = _prior_cov(g["B"], g["centers"], ppc, float(g["length_scale"]), float(g["output_variance"]))
+    assert rel_err(cov, g["cov_theta"]) < 1e-12
+    centers = np.mean(cell_vertices(nc)[:, :, :ndim], axis=1)        # Tessellation.get_cell_centers
+    assert np.allclose(centers, g["centers"], rtol=0, atol=1e-15)
+    As = (g["B"].astype(np.float32) @ g["theta"][0].astype(np.float32)).reshape(-1, ndim, ndim + 1)
+    cells = O.findcellidx(g["grid"], nc)
+    homog = np.concatenate([g["grid"], np.ones((1, g["grid"].shape[1]), np.float32)])
+    v = np.einsum("pij,jp->ip", As[cells], homog)
+    # zero-boundary fields cancel (|a x|, |b| >> |v| = |a x + b|): float32 evaluation order shows at 1e-5
+    assert rel_err(v, g["vectorfield"]) < 2e-5
