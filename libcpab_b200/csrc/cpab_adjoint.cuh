@@ -246,6 +246,11 @@ struct Sweep {
         bool failed = false;
         float m = m0;                  // certificate bound M_n of the current step (local units)
         int c_first = 0;
+        // MODE 2 reads its velocity fields through L1 (every lane its own theta): the block of the
+        // current cell stays in registers and is re-fetched only when the trajectory changes cell
+        // (1-2 % of the steps) -- the dependent global load per step was the kernel's main stall
+        T a_held[PPC];
+        int c_held = -1;
         if (MODE == 1) c_first = find_cell<NDIM>(p, g);
         auto segment = [&](int sg, auto full_tag) {     // FULL = a whole segment that is not the last one: no bounds checks
             constexpr bool FULL = decltype(full_tag)::value;
@@ -268,9 +273,8 @@ struct Sweep {
                     else ct16[n * stride + slot] = (unsigned short)c;
                     if (FULL || n + 1 < nsteps) {
                         if constexpr (MODE == 2) {
-                            T a[PPC];
-                            load_affine<NDIM>(Ag + (size_t)c * PPC, a);
-                            step_reference<NDIM>(a, 1.0 / nsteps, p);
+                            if (c != c_held) { load_affine<NDIM>(Ag + (size_t)c * PPC, a_held); c_held = c; }
+                            step_reference<NDIM>(a_held, 1.0 / nsteps, p);
                         } else {
                             T w[WS];
                             table.load(c, w);
@@ -290,10 +294,23 @@ struct Sweep {
     // ---- pass 2: segments in reverse; replay p into registers (no search), sweep lambda back,
     //      accumulate R_c += lambda_{n+1} [p_n;1]^T per thread and hand a cell's sum to R[theta]
     //      (Gt) when the trajectory leaves the cell.  Leaves lambda_0 in lam.
-    template <typename Table>
+    //      KEEP: the record of the current cell is held in registers across steps and re-fetched only
+    //      on a cell change (tables read through L1, k_backward_redo); staged tables re-read it.
+    template <bool KEEP = false, typename Table>
     __device__ __forceinline__ void pass2(const Table& table, T* Gt, T* lam, T* acc, int& cur) const
     {
         T p[NDIM];
+        T wk[WS];
+        int wc = -1;
+        auto fetch = [&](int c, T* w) {
+            if constexpr (KEEP) {
+                if (c != wc) { table.load(c, wk); wc = c; }
+#pragma unroll
+                for (int e = 0; e < WS; ++e) w[e] = wk[e];
+            } else {
+                table.load(c, w);
+            }
+        };
         auto segment = [&](int sg, auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
             const int len = FULL ? SEG : nsteps - sg * SEG;
@@ -310,7 +327,7 @@ struct Sweep {
 #pragma unroll
                     for (int j = 0; j < NDIM; ++j) ps[s][j] = p[j];
                     if (s + 1 < SEG && (FULL || s + 1 < len)) {
-                        table.load(cs[s], w);       // (the compiler keeps these for the sweep below)
+                        fetch(cs[s], w);            // (the compiler keeps these for the sweep below)
                         step_inc<NDIM>(w, p);
                     }
                 }
@@ -319,7 +336,7 @@ struct Sweep {
             for (int s = SEG - 1; s >= 0; --s) {
                 if (FULL || s < len) {
                     const int c = cs[s];
-                    table.load(c, w);
+                    fetch(c, w);
                     if (c != cur) {                 // left a cell: hand its sum to R[theta]
                         if (cur >= 0) red_cell<PPC>(Gt + (size_t)cur * PPC, acc);
 #pragma unroll
@@ -481,7 +498,7 @@ k_backward(const T* __restrict__ points, const T* __restrict__ Ws, const T* __re
 // registers) spill and run 30 % slower; chunks of 4 mask words: 1 or 2 cost more draws than they
 // save in tail (0.69 / 0.77 / 1.01 ms for 4 / 2 / 1 words on 128 thetas x 512^2)
 #ifndef CPAB_REDO_CTAS
-#define CPAB_REDO_CTAS 6
+#define CPAB_REDO_CTAS 4
 #endif
 #ifndef CPAB_REDO_CHUNK
 #define CPAB_REDO_CHUNK 4
@@ -538,7 +555,7 @@ k_backward_redo(const float* __restrict__ points, const float* __restrict__ Ws, 
             const T* Ag = reinterpret_cast<const T*>(ca.As) + (size_t)theta * tsize;
             sw.template pass1<2>(g, gtab, Ag, 0.0f, 0.0f, 0.0f, p);
             T* Gt = G + (size_t)theta * tsize;
-            sw.pass2(gtab, Gt, lam, acc, cur);
+            sw.template pass2<true>(gtab, Gt, lam, acc, cur);
             if (dpoints != nullptr) {
                 T* dp = dpoints + (size_t)theta * NDIM * nP;
 #pragma unroll

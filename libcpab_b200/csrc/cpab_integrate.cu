@@ -328,7 +328,7 @@ int set_tuning(const char* key, int value)
     if (k == "bwd_seg" && (value == 0 || value == 3 || value == 5 || value == 10)) { t.bwd_seg = value; return kOk; }
     if (k == "bwd_stage" && value >= -1 && value <= 1) { t.bwd_stage = value; return kOk; }
     if (k == "bwd_block" && (value == 64 || value == 128 || value == 256)) { t.bwd_block = value; return kOk; }
-    if (k == "interp_variant" && value >= 0 && value <= 8) { set_interp_variant(value); return kOk; }
+    if (k == "interp_variant" && value >= 0 && value <= 14) { set_interp_variant(value); return kOk; }
     if (k == "interp_max_ctas" && value >= 0) { set_interp_max_ctas(value); return kOk; }
     set_error("unknown tuning key/value %s=%d", key, value);
     return kErrArgument;

@@ -25,7 +25,7 @@ namespace cpab {
 namespace {
 
 int g_interp_max_ctas = 0;  // tests: cap the persistent grid so that every CTA walks over many tiles ("interp_max_ctas")
-int g_interp_variant = 5;   // 0-4: one tile per CTA (0: 4 points in flight, 1 CTA/SM target; 1: 2 / 6; 2: 1 / 8); 5-8: persistent pipelined kernels (float32; default 5) (cpab_b200_set_tuning "interp_variant")
+int g_interp_variant = 9;   // 0-4: one tile per CTA (0: 4 points in flight, 1 CTA/SM target; 1: 2 / 6; 2: 1 / 8); 5-8: persistent kernels, grid tiles prefetched; 9-11: + texel loads software-pipelined in registers (single channel; default 9); 12-14: measurement probes (cpab_b200_set_tuning "interp_variant")
 
 // ---------------------------------------------------------------------------------------------
 // forward.  NDIM >= 2: CTA = 256 threads, tile 32 (first index) x 32 (last index);
@@ -372,7 +372,10 @@ __device__ __forceinline__ void prefetch_grid_tile(const float* __restrict__ gri
     cp_async_commit();      // (an empty group when there is no tile: keeps the group count uniform)
 }
 
-template <int NDIM, bool FULL, bool ONECH>
+// PROBE != 0: measurement-only variants that keep the traffic and drop parts of the work (tools/interp_variants.py):
+// 1 = no texel access at all (out = gx + gy), 2 = one aligned texel load at the identity position,
+// 3 = four texel loads around the identity position (no tap arithmetic).  Never used by the product.
+template <int NDIM, bool FULL, bool ONECH, int PROBE = 0>
 __device__ __forceinline__ void interp_fwd_compute(const float* __restrict__ data, float* __restrict__ out, const Shape& s,
                                                    const TilePos& tp, uint32_t sg)
 {
@@ -390,6 +393,20 @@ __device__ __forceinline__ void interp_fwd_compute(const float* __restrict__ dat
     float gc[NDIM][4];
 #pragma unroll
     for (int j = 0; j < NDIM; ++j) lds_f32x4(sg + 4u * (uint32_t)((j * TILE + lane) * PITCH + 4 * wrp), gc[j]);
+    if constexpr (PROBE != 0 && NDIM == 2) {
+        float r[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            r[b] = gc[0][b] + gc[1][b];
+            const int ia = min(iA + b, s.S[0] - 2), jf = min(iF, s.S[1] - 2);
+            const float* q = dn + ia * s.S[1] + jf;
+            if (PROBE == 2) r[b] += __ldg(q);
+            if (PROBE == 3) r[b] += (__ldg(q) + __ldg(q + 1)) + (__ldg(q + s.S[1]) + __ldg(q + s.S[1] + 1));
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (FULL || (iA + b < O0 && iF < OF)) on[b * ostride] = r[b];
+    } else {
     Taps<float, NDIM> tq[4];
     bool ok[4];
 #pragma unroll
@@ -412,9 +429,10 @@ __device__ __forceinline__ void interp_fwd_compute(const float* __restrict__ dat
         for (int b = 0; b < 4; ++b)
             if (FULL || ok[b]) op[b * ostride] = blend<NDIM>(v[b], tq[b].w);
     }
+    }
 }
 
-template <int NDIM, int MINB, bool ONECH>
+template <int NDIM, int MINB, bool ONECH, int PROBE = 0>
 __global__ void __launch_bounds__(256, MINB)
 k_interp_fwd_pipe(const float* __restrict__ data, const float* __restrict__ grid, float* __restrict__ out,
                   const __grid_constant__ Shape s, const __grid_constant__ TileGeom tg)
@@ -438,9 +456,104 @@ k_interp_fwd_pipe(const float* __restrict__ data, const float* __restrict__ grid
         const TilePos tp = cur.pos();
         const bool full = (tp.a0 + TILE <= s.O[0]) && (tp.f0 + TILE <= s.O[NDIM - 1]);
         const uint32_t sg = ring + 4u * (uint32_t)(stage * STAGE);
-        if (full) interp_fwd_compute<NDIM, true, ONECH>(data, out, s, tp, sg);
-        else interp_fwd_compute<NDIM, false, ONECH>(data, out, s, tp, sg);
+        if (full) interp_fwd_compute<NDIM, true, ONECH, PROBE>(data, out, s, tp, sg);
+        else interp_fwd_compute<NDIM, false, ONECH, PROBE>(data, out, s, tp, sg);
         stage = stage + 1 == kStages ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, single channel (the default for C == 1), software-pipelined in REGISTERS: the texel
+// loads of tile i+1 are issued before tile i is blended, so a thread has up to 2 x 16 gathers in
+// flight and a tile's gather latency overlaps the previous tile's arithmetic and stores.  Two
+// register sets alternate (the loop is unrolled by two, no moves).  Loads are unconditional
+// (clamped grid coordinates give valid addresses everywhere), only the stores of edge tiles are
+// predicated.  Measured on 128 x 512^2 (profiles/r02_interp_variants.txt): the skeleton alone (no
+// texel access) streams at 5.6 TB/s; with the gather exposed once per tile (k_interp_fwd_pipe)
+// 4.0 TB/s; with this pipeline 4.95 TB/s.  (Gathers through cp.async into a second shared ring --
+// more loads in flight at no register cost -- were slower: 3.3 TB/s, 4-byte LDGSTS are expensive.)
+// ---------------------------------------------------------------------------------------------
+template <int NDIM, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_interp_fwd_sw(const float* __restrict__ data, const float* __restrict__ grid, float* __restrict__ out,
+                const __grid_constant__ Shape s, const __grid_constant__ TileGeom tg)
+{
+    constexpr int NC = 1 << NDIM;
+    constexpr int GSTAGE = NDIM * TILE * PITCH;
+    extern __shared__ __align__(16) float sg_ring[];
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sg_ring);
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int O0 = s.O[0], OF = s.O[NDIM - 1];
+    const int nP = O0 * s.O[1] * (NDIM >= 3 ? s.O[2] : 1);
+    const int plane = s.S[0] * s.S[1] * (NDIM >= 3 ? s.S[2] : 1);
+    const int ostride = NDIM == 2 ? s.O[1] : s.O[1] * s.O[2];
+    const uint32_t mine = ring + 4u * (uint32_t)(lane * PITCH + 4 * wrp);
+
+    TileCursor cur, nx, pf;
+    cur.init(blockIdx.x, tg);
+    pf = cur;
+    int gstage = 0;
+
+    auto load_tile = [&](const TileCursor& c, int gs, float (&v)[4][NC], float (&w)[4][NDIM]) {
+        if (c.n >= s.N) return;
+        const float* dn = data + (size_t)c.n * plane;
+        asm volatile("" : "+l"(dn));
+        float gc[NDIM][4];
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) lds_f32x4(mine + 4u * (uint32_t)(gs * GSTAGE + j * TILE * PITCH), gc[j]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float g1[NDIM];
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) g1[j] = gc[j][b];
+            const Taps<float, NDIM> tq = make_taps<float, NDIM>(g1, s);
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) w[b][j] = tq.w[j];
+            gather<float, NDIM>(dn, tq, v[b]);
+        }
+    };
+    auto blend_tile = [&](const TileCursor& c, const float (&v)[4][NC], const float (&w)[4][NDIM]) {
+        const TilePos tp = c.pos();
+        const int iF = tp.f0 + lane, iA = tp.a0 + 4 * wrp;
+        float* on = out + (size_t)tp.n * nP + (NDIM == 2 ? iA * s.O[1] + iF : (iA * s.O[1] + tp.im) * s.O[2] + iF);
+        const bool full = (tp.a0 + TILE <= O0) && (tp.f0 + TILE <= OF);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const float r = blend<NDIM>(v[b], w[b]);
+            if (full || (iA + b < O0 && iF < OF)) on[b * ostride] = r;
+        }
+    };
+    // one pipeline step: the grid of tile `nx` has landed -> issue its texel loads into (vn, wn);
+    // refill the grid ring; blend tile `cur` from (vc, wc)
+    auto step = [&](float (&vc)[4][NC], float (&wc)[4][NDIM], float (&vn)[4][NC], float (&wn)[4][NDIM]) {
+        cp_async_wait<1>();
+        __syncthreads();
+        const int g1s = gstage + 1 == kStages ? 0 : gstage + 1;
+        load_tile(nx, g1s, vn, wn);
+        pf.advance(tg);
+        prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * (uint32_t)(gstage * GSTAGE));
+        blend_tile(cur, vc, wc);
+        gstage = g1s;
+        cur = nx;
+        nx.advance(tg);
+    };
+
+    float vA[4][NC], wA[4][NDIM], vB[4][NC], wB[4][NDIM];
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring);
+    pf.advance(tg);
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * GSTAGE);
+    pf.advance(tg);
+    cp_async_wait<1>();
+    __syncthreads();
+    load_tile(cur, 0, vA, wA);
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * 2 * GSTAGE);
+    nx = cur;
+    nx.advance(tg);
+    while (cur.n < s.N) {
+        step(vA, wA, vB, wB);
+        if (cur.n >= s.N) break;
+        step(vB, wB, vA, wA);
     }
     cp_async_wait<0>();
 }
@@ -572,8 +685,115 @@ k_interp_bwd_pipe(const float* __restrict__ data, const float* __restrict__ grid
     cp_async_wait<0>();
 }
 
+// Backward w.r.t. the grid, single channel, no d/d(data): the same register software pipeline.  The
+// d/dgrid tile leaves through a stage of its own (the grid ring is being refilled meanwhile).
+template <int NDIM, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_interp_bwd_sw(const float* __restrict__ data, const float* __restrict__ grid, const float* __restrict__ gout,
+                float* __restrict__ dgrid, const __grid_constant__ Shape s, const __grid_constant__ TileGeom tg)
+{
+    constexpr int NC = 1 << NDIM;
+    constexpr int GSTAGE = NDIM * TILE * PITCH;
+    extern __shared__ __align__(16) float sg_ring[];       // [kStages][GSTAGE] grid ring | [GSTAGE] d/dgrid staging
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sg_ring);
+    const uint32_t ostage = ring + 4u * (uint32_t)(kStages * GSTAGE);
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int O0 = s.O[0], OF = s.O[NDIM - 1];
+    const int nP = O0 * s.O[1] * (NDIM >= 3 ? s.O[2] : 1);
+    const int plane = s.S[0] * s.S[1] * (NDIM >= 3 ? s.S[2] : 1);
+    const int ostride = NDIM == 2 ? s.O[1] : s.O[1] * s.O[2];
+    const uint32_t mine = 4u * (uint32_t)(lane * PITCH + 4 * wrp);
+    float scale[NDIM];                  // xd = x - x0 with x = g*(size-1): d/dg = size-1
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) scale[j] = (float)(s.S[j] - 1);
+
+    TileCursor cur, nx, pf;
+    cur.init(blockIdx.x, tg);
+    pf = cur;
+    int gstage = 0;
+
+    auto load_tile = [&](const TileCursor& c, int gs, float (&v)[4][NC], float (&w)[4][NDIM], float (&g)[4]) {
+        if (c.n >= s.N) return;
+        const TilePos tp = c.pos();
+        const float* dn = data + (size_t)c.n * plane;
+        asm volatile("" : "+l"(dn));
+        // upstream gradient: clamped like the grid chunks (edge tiles read valid, unused values)
+        const int iF = min(tp.f0 + lane, OF - 1), iA = tp.a0 + 4 * wrp;
+        const float* gp = gout + (size_t)tp.n * nP + (NDIM == 2 ? iF : tp.im * s.O[2] + iF);
+        float gc[NDIM][4];
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) lds_f32x4(ring + mine + 4u * (uint32_t)(gs * GSTAGE + j * TILE * PITCH), gc[j]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float g1[NDIM];
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) g1[j] = gc[j][b];
+            const Taps<float, NDIM> tq = make_taps<float, NDIM>(g1, s);
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) w[b][j] = tq.w[j];
+            gather<float, NDIM>(dn, tq, v[b]);
+            g[b] = __ldg(gp + (size_t)min(iA + b, O0 - 1) * ostride);
+        }
+    };
+    auto finish_tile = [&](const TileCursor& c, const float (&v)[4][NC], const float (&w)[4][NDIM], const float (&g)[4]) {
+        const TilePos tp = c.pos();
+        float dg[NDIM][4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float gv[NC], dw[NDIM];
+            blend_vjp<NDIM>(v[b], w[b], g[b], gv, dw);
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) dg[j][b] = dw[j] * scale[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) sts_f32x4(ostage + mine + 4u * (uint32_t)(j * TILE * PITCH), dg[j]);
+        __syncthreads();
+        const int row = threadIdx.x >> 3, ch = threadIdx.x & 7;
+        if (tp.a0 + 4 * ch < O0 && tp.f0 + row < OF) {
+            float* dst = dgrid + chunk_offset<NDIM>(s, tp);
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) {
+                float t[4];
+                lds_f32x4(ostage + 4u * (uint32_t)((j * TILE + row) * PITCH + 4 * ch), t);
+                *reinterpret_cast<float4*>(dst + (size_t)j * nP) = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    };
+    auto step = [&](float (&vc)[4][NC], float (&wc)[4][NDIM], float (&gc_)[4],
+                    float (&vn)[4][NC], float (&wn)[4][NDIM], float (&gn)[4]) {
+        cp_async_wait<1>();
+        __syncthreads();
+        const int g1s = gstage + 1 == kStages ? 0 : gstage + 1;
+        load_tile(nx, g1s, vn, wn, gn);
+        pf.advance(tg);
+        prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * (uint32_t)(gstage * GSTAGE));
+        finish_tile(cur, vc, wc, gc_);
+        gstage = g1s;
+        cur = nx;
+        nx.advance(tg);
+    };
+
+    float vA[4][NC], wA[4][NDIM], gA[4], vB[4][NC], wB[4][NDIM], gB[4];
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring);
+    pf.advance(tg);
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * GSTAGE);
+    pf.advance(tg);
+    cp_async_wait<1>();
+    __syncthreads();
+    load_tile(cur, 0, vA, wA, gA);
+    prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * 2 * GSTAGE);
+    nx = cur;
+    nx.advance(tg);
+    while (cur.n < s.N) {
+        step(vA, wA, gA, vB, wB, gB);
+        if (cur.n >= s.N) break;
+        step(vB, wB, gB, vA, wA, gA);
+    }
+    cp_async_wait<0>();
+}
+
 template <typename KERN, typename... Args>
-static int launch_pipe(KERN kern, int ndim, const Shape& s, cudaStream_t st, int slot, Args... args)
+static int launch_pipe(KERN kern, int ndim, const Shape& s, cudaStream_t st, int slot, size_t extra_smem, Args... args)
 {
     TileGeom tg;
     tg.tiles_a = (s.O[0] + TILE - 1) / TILE;
@@ -581,7 +801,7 @@ static int launch_pipe(KERN kern, int ndim, const Shape& s, cudaStream_t st, int
     tg.mid = ndim == 3 ? s.O[1] : 1;
     const long long total = (long long)s.N * tg.mid * tg.tiles_f * tg.tiles_a;
     if (total >= (1LL << 31)) { set_error("interpolate: %lld tiles exceed 2^31", total); return kErrUnsupported; }
-    const size_t smem = (size_t)kStages * ndim * TILE * PITCH * sizeof(float);
+    const size_t smem = (size_t)kStages * ndim * TILE * PITCH * sizeof(float) + extra_smem;
     if (smem > 48 * 1024) CPAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0, dev = 0, sms = 0;
     CPAB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
@@ -692,8 +912,7 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
         }
     }
     if constexpr (sizeof(T) == 4) {
-        // persistent, pipelined kernels (variants 5-8: resident CTAs targeted / points whose gathers
-        // are in flight together in the backward); they move 16-byte chunks of the grid, which
+        // persistent, pipelined kernels (variants >= 5); they move 16-byte chunks of the grid, which
         // needs 16-byte aligned planes -- anything else takes the one-tile-per-CTA kernels
         const int var = g_interp_variant;
         const float* d = (const float*)data; const float* gr = (const float*)grid; const float* go = (const float*)gout;
@@ -701,9 +920,32 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
         const bool aligned = s.O[0] % 4 == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0 &&
                              (!backward || out_or_dgrid == nullptr || (reinterpret_cast<uintptr_t>(out_or_dgrid) & 15) == 0);
         if (var >= 5 && aligned) {
-#define FWD(ND, M) (s.C == 1 ? launch_pipe(k_interp_fwd_pipe<ND, M, true>, ndim, s, st, kProfInterpFwd, d, gr, o) \
-                             : launch_pipe(k_interp_fwd_pipe<ND, M, false>, ndim, s, st, kProfInterpFwd, d, gr, o))
-#define BWD(ND, B, M) launch_pipe(k_interp_bwd_pipe<ND, B, M>, ndim, s, st, kProfInterpBwd, d, gr, go, o, dd)
+#define FWD(ND, M) (s.C == 1 ? launch_pipe(k_interp_fwd_pipe<ND, M, true>, ndim, s, st, kProfInterpFwd, 0, d, gr, o) \
+                             : launch_pipe(k_interp_fwd_pipe<ND, M, false>, ndim, s, st, kProfInterpFwd, 0, d, gr, o))
+#define BWD(ND, B, M) launch_pipe(k_interp_bwd_pipe<ND, B, M>, ndim, s, st, kProfInterpBwd, 0, d, gr, go, o, dd)
+            if (!backward && s.C == 1 && ndim == 2 && var >= 12) {      // measurement probes (see interp_fwd_compute)
+                if (var == 12) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 1>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
+                if (var == 13) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 2>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
+                return launch_pipe(k_interp_fwd_pipe<2, 4, true, 3>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
+            }
+            if (!backward && s.C == 1 && ndim == 2 && var >= 12) {      // measurement probes (see interp_fwd_compute)
+                if (var == 12) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 1>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
+                if (var == 13) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 2>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
+                return launch_pipe(k_interp_fwd_pipe<2, 4, true, 3>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
+            }
+            // 9-11: register software pipeline (single channel; backward: d/dgrid only)
+            if (backward && s.C == 1 && dd == nullptr && o != nullptr && var >= 9) {
+#define BWDS(ND, M) launch_pipe(k_interp_bwd_sw<ND, M>, ndim, s, st, kProfInterpBwd, (size_t)ND * TILE * PITCH * sizeof(float), d, gr, go, o)
+                if (ndim == 2) return var == 9 ? BWDS(2, 3) : var == 10 ? BWDS(2, 2) : BWDS(2, 4);
+                return var == 9 ? BWDS(3, 2) : BWDS(3, 1);
+#undef BWDS
+            }
+            if (!backward && s.C == 1 && var >= 9) {
+#define FWDS(ND, M) launch_pipe(k_interp_fwd_sw<ND, M>, ndim, s, st, kProfInterpFwd, 0, d, gr, o)
+                if (ndim == 2) return var == 9 ? FWDS(2, 3) : var == 10 ? FWDS(2, 2) : FWDS(2, 4);
+                return var == 9 ? FWDS(3, 2) : FWDS(3, 1);
+#undef FWDS
+            }
             if (ndim == 2) {
                 if (!backward) return var == 5 ? FWD(2, 4) : var == 6 ? FWD(2, 5) : var == 7 ? FWD(2, 6) : FWD(2, 3);
                 return var == 5 ? BWD(2, 2, 4) : var == 6 ? BWD(2, 4, 3) : var == 7 ? BWD(2, 1, 5) : BWD(2, 4, 2);

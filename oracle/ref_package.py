@@ -60,8 +60,8 @@ def import_with_b200_backend():
     sys.modules.setdefault("matplotlib.pyplot", plt)
     scipy.transpose = np.transpose
     scipy.compress = np.compress
-    if not hasattr(torch, "solve"):
-        torch.solve = lambda B, A: (torch.linalg.solve(A, B), None)
+    # torch.solve survives only as a stub that raises (pytorch/expm.py:27 calls it); solve(B, A) solved A X = B
+    torch.solve = lambda B, A: (torch.linalg.solve(A, B), None)
     if not hasattr(np, "bool"):
         np.bool = bool
 

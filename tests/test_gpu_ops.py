@@ -396,7 +396,7 @@ def test_interpolate_persistent_kernels_walk_many_tiles(shape, outsize, cap):
     dg_o, dd_o = O.interpolate_vjp(data, grid, outsize, gout)
     try:
         _lib.set_tuning("interp_max_ctas", cap)
-        for var in (5, 6, 7, 8):
+        for var in (2, 5, 6, 7, 8, 9, 10, 11):
             _lib.set_tuning("interp_variant", var)
             out = ops.interpolate_forward(dev(data), dev(grid), outsize).cpu().numpy()
             assert np.array_equal(out, ref), var
@@ -407,7 +407,7 @@ def test_interpolate_persistent_kernels_walk_many_tiles(shape, outsize, cap):
             assert none is None and torch.equal(dgrid2, dgrid), var
     finally:
         _lib.set_tuning("interp_max_ctas", 0)
-        _lib.set_tuning("interp_variant", 5)
+        _lib.set_tuning("interp_variant", 9)
 
 
 def test_interpolate_taps_extreme_coordinates():
