@@ -56,6 +56,10 @@ struct Geom {
     float hi2[3];       // 2-D: fast-path clamp (<= spanm, estimate there is exact)
     float band2;        // 2-D: guard band of the diagonal tests
     float hi3[3];       // 3-D: clamp bound (float)(n*inc - 1e-8); z uses inc_x (cpab_ops.cpp:141)
+    float top3[3];      // 3-D lean path: largest coordinate it accepts (x, y: min(1, hi3); z: hi3)
+    float ctop3[3];     // 3-D lean path: largest coordinate at which the one-sided estimate is still cell n-1
+    float band3;        // 3-D: guard band of the separating-plane tests
+    int clamp3;         // 3-D lean path: ctop3 < top3 on some axis (the estimate needs the clamp)
     // ---- float64 check mode -------------------------------------------------------------------
     double wd[3];       // 1.0 / n
     double spand[3];    // n * wd
@@ -121,6 +125,30 @@ inline Geom make_geom(int ndim, const int* nc)
         g.hi3[j] = (float)((double)((float)g.nc[j] * g.w[wsel]) - 1e-8);
         g.hi3d[j] = g.nc[j] * g.wd[wsel] - 1e-8;
     }
+    // 3-D lean path (find_cell_3d_lean): accepted coordinate range and, where the cell width is
+    // rounded up (n*w > 1: floor(1/w) = n-1 but floor(1*nup) = n), the clamp below which the
+    // one-sided estimate stays in the last cell -- zero-boundary flows park points on the upper
+    // faces, they must not take the rare path on every step.  The clamp moves a local coordinate
+    // by at most (top - ctop)*n; the guard band of the plane tests grows by three times that.
+    float edge3 = 0.0f;
+    g.clamp3 = 0;
+    for (int j = 0; j < 3; ++j) {
+        g.top3[j] = j < 2 ? fminf(1.0f, g.hi3[j]) : g.hi3[j];
+        float c = g.top3[j];
+        const bool up = (double)g.nc[j] * (double)g.w[j] > (double)g.top3[j];      // true floor(top/w) is n-1
+        if (up) {
+            for (int it = 0; it < 64; ++it) {
+                const double kest = floor((double)c * (double)g.nup[j]);
+                if (kest <= (double)(g.nc[j] - 1) && (double)c - kest * (double)g.w[j] >= 0.0) break;
+                c = nextafterf(c, 0.0f);
+            }
+        }
+        g.ctop3[j] = c;
+        if (c < g.top3[j]) g.clamp3 = 1;
+        const float gap = (g.top3[j] - c) * g.nf[j];
+        if (gap > edge3) edge3 = gap;
+    }
+    g.band3 = 4e-6f + 3.0f * edge3;
     return g;
 }
 
@@ -446,11 +474,86 @@ CPAB_HD bool find_cell_3d_fast(float p0, float p1, float p2, const Geom& g, int&
     return find_cell_3d_fast_t<false>(p0, p1, p2, g, cell, q, dist);
 }
 
-CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g)
+// Complete search, out of line: the previous fast path (handles the outside-the-box push and the
+// clamps inline) with the exact replay behind it.  The integration loops reach it only through the
+// warp vote of find_cell_3d_lean.
+CPAB_HD_NOINLINE int find_cell_3d_full(float p0, float p1, float p2, const Geom& g)
 {
     int cell;
     float q[3];
     if (find_cell_3d_fast(p0, p1, p2, g, cell, q)) return find_cell_3d_replay<float>(q[0], q[1], q[2], g);
+    return cell;
+}
+
+// Lean 3-D fast path (the 2-D scheme on three axes).  Handles ONLY points with every coordinate in
+// [0, top]: no outside-the-box push, no lower clamp; the reference's upper clamp and its
+// `mymin(n-1, .)` are reproduced by min(k, n-1) (a coordinate of exactly 1.0 keeps local
+// coordinate 0 in the last cube -- the reference's own quirk).  One-sided column
+// estimates as in divmod_up (x, y packed, z scalar): floor(c * nup) is the exact column or one
+// more, r = fma(-k, w, c) is exact and negative exactly in the second case.  Parity swap, the four
+// separating planes in the reference's order; since the corner tetrahedra are disjoint, outside
+// the guard band at most one of t1..t4 is non-negative and the index is 10 - sum_i i*sign(t_i).
+// Returns true when the point needs find_cell_3d_full instead: a coordinate outside [0, top] (or
+// NaN), an estimate one too large, or a point within the band of a plane.  ~50 instructions against
+// ~100 of find_cell_3d_fast_t.  NEAR: also the certificate's `dist` (see find_cell_near).
+template <bool NEAR>
+CPAB_HD bool find_cell_3d_lean(float q0, float q1, float q2, const Geom& g, float magic, int& cell, float& dist)
+{
+    const float lo = fminf(fminf(q0, q1), q2);
+    const float hi = fminf(fminf(g.top3[0] - q0, g.top3[1] - q1), g.top3[2] - q2);
+    // (ctop3 == top3 where no clamp is needed: unconditional, a data-dependent select would cost more)
+    const float c0 = fminf(q0, g.ctop3[0]), c1 = fminf(q1, g.ctop3[1]), c2 = fminf(q2, g.ctop3[2]);
+    float kx, ky, kz, rx, ry, rz, x, y, z;
+#if defined(__CUDA_ARCH__)
+    {
+        const F2 pc = pk(c0, c1), mg = bc(magic);
+        const F2 kf = sub2(fma2_rm(pc, pk(g.nup[0], g.nup[1]), mg), mg);
+        const F2 r = fma2(kf, pk(-g.w[0], -g.w[1]), pc);
+        const F2 xy = mul2(r, pk(g.nf[0], g.nf[1]));
+        unpk(kf, kx, ky);
+        unpk(r, rx, ry);
+        unpk(xy, x, y);
+    }
+#else
+    divmod_up(c0, g.nup[0], g.w[0], magic, kx, rx);
+    divmod_up(c1, g.nup[1], g.w[1], magic, ky, ry);
+    x = rx * g.nf[0];
+    y = ry * g.nf[1];
+#endif
+    divmod_up(c2, g.nup[2], g.w[2], magic, kz, rz);
+    z = rz * g.nf[2];
+    const float rmin = fminf(fminf(rx, ry), rz);
+    kx = fminf(kx, g.nm1[0]);
+    ky = fminf(ky, g.nm1[1]);
+    kz = fminf(kz, g.nm1[2]);
+    const int cube = (int)fmaf(fmaf(kz, g.nf[1], ky), g.nf[0], kx);
+    const int par = (int)((kx + ky) + kz);
+    if (par & 1) { const float t = x; x = y; y = 1.0f - t; }
+    const float s = x + y, u = y - x;
+    const float t1 = z - s, t2 = (s + z) - 2.0f, t3 = u - z, t4 = -u - z;
+    const float nearest = fminf(fminf(fabsf(t1), fabsf(t2)), fminf(fabsf(t3), fabsf(t4)));
+#if defined(__CUDA_ARCH__)
+    const int neg = (int)((unsigned)__float_as_int(t1) >> 31) + 2 * (int)((unsigned)__float_as_int(t2) >> 31) +
+                    3 * (int)((unsigned)__float_as_int(t3) >> 31) + 4 * (int)((unsigned)__float_as_int(t4) >> 31);
+    const int tet = 10 - neg;
+#else
+    const int tet = (t1 >= 0.0f ? 1 : 0) + (t2 >= 0.0f ? 2 : 0) + (t3 >= 0.0f ? 3 : 0) + (t4 >= 0.0f ? 4 : 0);
+#endif
+    cell = 5 * cube + tet;
+    // (negated >=: a NaN coordinate makes `nearest` NaN -- every plane involves all three -- and must leave)
+    const bool rare = !(fminf(fminf(lo, hi), rmin) >= 0.0f) | !(nearest >= g.band3);
+    if (NEAR) {
+        const float lo3 = fminf(fminf(x, y), z), hi3 = fmaxf(fmaxf(x, y), z);
+        dist = rare ? -1.0f : fminf(nearest, fminf(lo3, 1.0f - hi3));
+    }
+    return rare;
+}
+
+CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g, float magic = 12582912.0f)
+{
+    int cell;
+    float dist;
+    if (find_cell_3d_lean<false>(p0, p1, p2, g, magic, cell, dist)) return find_cell_3d_full(p0, p1, p2, g);
     return cell;
 }
 
@@ -533,21 +636,20 @@ CPAB_HD float cert_scale(const Geom& g)
 // in local units (an iterate whose pre-rounding value reaches the domain boundary is then flagged)
 CPAB_HD float cert_floor(const Geom& g)
 {
-    const float band = g.ndim == 1 ? 4.0f * 5.9604645e-08f * g.nf[0] : g.ndim == 2 ? g.band2 : 4e-6f;
+    const float band = g.ndim == 1 ? 4.0f * 5.9604645e-08f * g.nf[0] : g.ndim == 2 ? g.band2 : g.band3;
     return band + 1.1920929e-07f * cert_scale(g);
 }
-CPAB_HD int find_cell_3d_near(float p0, float p1, float p2, const Geom& g, float& dist)
+CPAB_HD int find_cell_3d_near(float p0, float p1, float p2, const Geom& g, float magic, float& dist)
 {
     int cell;
-    float q[3];
-    find_cell_3d_fast_t<true>(p0, p1, p2, g, cell, q, dist);
+    find_cell_3d_lean<true>(p0, p1, p2, g, magic, cell, dist);     // dist = -1 wherever the lean path does not apply
     return cell;
 }
 template <int NDIM> CPAB_HD int find_cell_near(const float* p, const Geom& g, float magic, float& dist)
 {
     if (NDIM == 1) return find_cell_1d_near(p[0], g, magic, dist);
     if (NDIM == 2) return find_cell_2d_near(p[0], p[1], g, magic, dist);
-    return find_cell_3d_near(p[0], p[1], p[2], g, dist);
+    return find_cell_3d_near(p[0], p[1], p[2], g, magic, dist);
 }
 template <int NDIM> CPAB_HD int find_cell_near(const double* p, const Geom& g, float, float& dist);   // float32 only
 
@@ -579,14 +681,14 @@ struct CellEst { float kx, rx, ky, ry; };
 template <int NDIM> CPAB_HD bool find_cell_try(const float* p, const Geom& g, float magic, int& cell, CellEst& est)
 {
     if (NDIM == 2) return find_cell_2d_fast(p[0], p[1], g, magic, cell, est.kx, est.rx, est.ky, est.ry);
-    if (NDIM == 3) { float q[3]; return find_cell_3d_fast(p[0], p[1], p[2], g, cell, q); }
+    if (NDIM == 3) { float dist; return find_cell_3d_lean<false>(p[0], p[1], p[2], g, magic, cell, dist); }
     cell = find_cell<NDIM, float>(p, g);
     return false;
 }
 template <int NDIM> CPAB_HD int find_cell_finish(const float* p, const Geom& g, const CellEst& est)
 {
     if (NDIM == 2) return find_cell_2d_rare(p[0], p[1], est.kx, est.rx, est.ky, est.ry, g);
-    if (NDIM == 3) return find_cell<3, float>(p, g);
+    if (NDIM == 3) return find_cell_3d_full(p[0], p[1], p[2], g);
     return find_cell<NDIM, float>(p, g);
 }
 template <int NDIM> CPAB_HD bool find_cell_try(const double* p, const Geom& g, float, int& cell, CellEst&)

@@ -26,7 +26,14 @@ for tess, n, size, kw in cases:
     for var in (2, 5, 9, 10, 11, 12, 13, 14):
         _lib.set_tuning("interp_variant", var)
         ms = timeit(lambda: ops.interpolate_forward(data, gt, size))
-        print(json.dumps(dict(kind="fwd", tess=tess, n=n, variant=var, ms=round(ms, 4), gbps=round(pts * (4 * nd + 8) / ms / 1e6))), flush=True)
+        _lib.profile_enable(True)           # the same launches timed by the library's own event pairs (what bench.py reads)
+        for _ in range(5):
+            flush.add_(1); ops.interpolate_forward(data, gt, size)
+        torch.cuda.synchronize()
+        pms, pn = _lib.profile_read("interp_fwd")
+        _lib.profile_enable(False)
+        print(json.dumps(dict(kind="fwd", tess=tess, n=n, variant=var, ms=round(ms, 4), gbps=round(pts * (4 * nd + 8) / ms / 1e6),
+                              lib_event_ms=round(pms / max(pn, 1), 4))), flush=True)
         if var >= 12:
             continue
         ms = timeit(lambda: ops.interpolate_backward(data, gt, g2, True, False))
