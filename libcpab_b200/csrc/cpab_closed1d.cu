@@ -80,11 +80,15 @@ k_closed1d(const T* __restrict__ points, const T* __restrict__ As, const T* __re
         const T x0 = src[i];
         // ---- forward: walk the cells
         T x = x0, t = (T)1;
+        bool fixed = false;
         int c = find_cell_1d(x, g);
         for (int it = 0; it <= nc; ++it) {
             const T a = sA[2 * c], b = sA[2 * c + 1];
             const T v = a * x + b;
-            if (v == (T)0) { t = (T)0; break; }
+            // fixed point of the field: stay in this cell for the REMAINING time (psi(x, t) = x there, and
+            // psi_a = x t e^{at}, psi_b = t phi1(at) below are the correct sensitivities -- zeroing t
+            // would make dL/dtheta vanish at theta = 0, the usual identity initialisation)
+            if (v == (T)0) { fixed = true; break; }
             T xb = x;
             int cn = c;
             const T th = hit_time(x, a, v, c, nc, xb, cn);
@@ -94,7 +98,7 @@ k_closed1d(const T* __restrict__ points, const T* __restrict__ As, const T* __re
         const T am = sA[2 * c], bm = sA[2 * c + 1];
         const T zm = am * t;
         const T em = exp(zm);
-        const T xf = x * em + bm * t * phi1(zm);
+        const T xf = fixed ? x : x * em + bm * t * phi1(zm);      // (a fixed point stays put exactly, not up to the cancellation in psi)
         if (!BACKWARD) {
             out[(size_t)theta * nP + i] = xf;
             continue;

@@ -110,6 +110,10 @@ template <int M> __device__ __forceinline__ Mat<M> expm_pade13(Mat<M> A)
     fro = sqrt(fro);
     int nsq = 0;
     if (fro > 5.371920351148152) nsq = (int)ceil(log2(fro / 5.371920351148152));
+    // a diverged theta (an entry of +-inf, norm = +inf) would saturate the conversion to INT_MAX and
+    // run ~2^31 squarings per thread; beyond 2^1100 the scaling underflows anyway.  The result is
+    // then inf/NaN (0 * inf in the scaled matrix), which is what torch's expm gives as well.
+    if (nsq > 1100) nsq = 1100;
     if (nsq > 0) {
         const double sc = ldexp(1.0, -nsq);
 #pragma unroll

@@ -343,19 +343,31 @@ struct TileCursor {
     __device__ __forceinline__ TilePos pos() const { return TilePos{n, im, ta * TILE, tf * TILE}; }
 };
 
-// element offset (within one coordinate plane of sample n) of this thread's 16-byte chunk of the
-// tile at `tp`.  Rows / chunks beyond the image are clamped to its last row / chunk: those entries
-// hold valid but unused values, and no copy needs a predicate.
+// element offset of this thread's 16-byte chunk of the tile at `tp` within ONE SAMPLE's first
+// coordinate plane (32-bit: the host checks that a sample's grid has < 2^31 elements).  Rows /
+// chunks beyond the image are clamped to its last row / chunk: those entries hold valid but unused
+// values, and no copy needs a predicate.
 template <int NDIM>
-__device__ __forceinline__ size_t chunk_offset(const Shape& s, const TilePos& tp)
+__device__ __forceinline__ unsigned chunk_offset32(const Shape& s, const TilePos& tp)
 {
     const int row = threadIdx.x >> 3, ch = threadIdx.x & 7;
     const int O0 = s.O[0];
-    const unsigned pstride = (unsigned)(NDIM == 2 ? O0 : O0 * s.O[1]);
-    const unsigned nP = pstride * (unsigned)s.O[NDIM - 1];
+    const int pstride = NDIM == 2 ? O0 : O0 * s.O[1];
     const int ix = min(tp.a0 + 4 * ch, O0 - 4);
-    const unsigned f = (unsigned)min(tp.f0 + row, s.O[NDIM - 1] - 1);
-    return (size_t)tp.n * NDIM * nP + (size_t)pstride * f + (size_t)((NDIM == 3 ? O0 * tp.im : 0) + ix);
+    const int f = min(tp.f0 + row, s.O[NDIM - 1] - 1);
+    return (unsigned)(pstride * f + (NDIM == 3 ? O0 * tp.im : 0) + ix);
+}
+// start of sample n's grid (uniform)
+template <int NDIM>
+__device__ __forceinline__ size_t sample_offset(const Shape& s, int n)
+{
+    const unsigned nP = (unsigned)(s.O[0] * s.O[1] * (NDIM >= 3 ? s.O[2] : 1));
+    return (size_t)n * NDIM * nP;
+}
+template <int NDIM>
+__device__ __forceinline__ size_t chunk_offset(const Shape& s, const TilePos& tp)
+{
+    return sample_offset<NDIM>(s, tp.n) + chunk_offset32<NDIM>(s, tp);
 }
 
 template <int NDIM>
@@ -364,7 +376,8 @@ __device__ __forceinline__ void prefetch_grid_tile(const float* __restrict__ gri
 {
     if (cur.n < s.N) {
         const unsigned nP = (unsigned)(s.O[0] * s.O[1] * (NDIM >= 3 ? s.O[2] : 1));
-        const float* src = grid + chunk_offset<NDIM>(s, cur.pos());
+        const float* gn = grid + sample_offset<NDIM>(s, cur.n);               // uniform
+        const float* src = gn + chunk_offset32<NDIM>(s, cur.pos());           // + one 32-bit thread offset
         const uint32_t dst = sg + 4u * (uint32_t)((threadIdx.x >> 3) * PITCH + 4 * (threadIdx.x & 7));
 #pragma unroll
         for (int j = 0; j < NDIM; ++j) cp_async16(dst + 4u * (uint32_t)(j * TILE * PITCH), src + (size_t)j * nP);
@@ -464,15 +477,17 @@ k_interp_fwd_pipe(const float* __restrict__ data, const float* __restrict__ grid
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward, single channel (the default for C == 1), software-pipelined in REGISTERS: the texel
-// loads of tile i+1 are issued before tile i is blended, so a thread has up to 2 x 16 gathers in
-// flight and a tile's gather latency overlaps the previous tile's arithmetic and stores.  Two
+// Forward, single channel, software-pipelined in REGISTERS (variants 10-11; NOT the default): the
+// texel loads of tile i+1 are issued before tile i is blended, so a thread has up to 2 x 16 gathers
+// in flight and a tile's gather latency overlaps the previous tile's arithmetic and stores.  Two
 // register sets alternate (the loop is unrolled by two, no moves).  Loads are unconditional
 // (clamped grid coordinates give valid addresses everywhere), only the stores of edge tiles are
-// predicated.  Measured on 128 x 512^2 (profiles/r02_interp_variants.txt): the skeleton alone (no
-// texel access) streams at 5.6 TB/s; with the gather exposed once per tile (k_interp_fwd_pipe)
-// 4.0 TB/s; with this pipeline 4.95 TB/s.  (Gathers through cp.async into a second shared ring --
-// more loads in flight at no register cost -- were slower: 3.3 TB/s, 4-byte LDGSTS are expensive.)
+// predicated.  Measured on 128 x 512^2 (profiles/r02_interp_variants.txt): 3.74 TB/s against 4.03 for
+// k_interp_fwd_pipe -- the forward is limited by instruction issue (the skeleton alone, no texel
+// access, streams at 5.6 TB/s; one aligned texel load per point: 5.2; four: 4.3-4.9), not by exposed
+// latency, and this version executes ~12 % more instructions.  The same pipeline DOES pay in the
+// backward (k_interp_bwd_sw: 4.14 against 3.69 TB/s).  Gathers through cp.async into a second shared
+// ring -- more loads in flight at no register cost -- were slower still (3.3 TB/s) and were removed.
 // ---------------------------------------------------------------------------------------------
 template <int NDIM, int MINB>
 __global__ void __launch_bounds__(256, MINB)
@@ -933,32 +948,50 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
                 if (var == 13) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 2>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
                 return launch_pipe(k_interp_fwd_pipe<2, 4, true, 3>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
             }
-            // 9-11: register software pipeline (single channel; backward: d/dgrid only)
+            // 9-11: backward (single channel, d/dgrid only) with the register software pipeline; forward:
+            // 9 = the pipe kernel (measured best, profiles/r02_interp_variants.txt), 10-11 = software pipeline
             if (backward && s.C == 1 && dd == nullptr && o != nullptr && var >= 9) {
 #define BWDS(ND, M) launch_pipe(k_interp_bwd_sw<ND, M>, ndim, s, st, kProfInterpBwd, (size_t)ND * TILE * PITCH * sizeof(float), d, gr, go, o)
                 if (ndim == 2) return var == 9 ? BWDS(2, 3) : var == 10 ? BWDS(2, 2) : BWDS(2, 4);
                 return var == 9 ? BWDS(3, 2) : BWDS(3, 1);
 #undef BWDS
             }
-            if (!backward && s.C == 1 && var >= 9) {
+            if (!backward && s.C == 1 && var >= 10) {
 #define FWDS(ND, M) launch_pipe(k_interp_fwd_sw<ND, M>, ndim, s, st, kProfInterpFwd, 0, d, gr, o)
-                if (ndim == 2) return var == 9 ? FWDS(2, 3) : var == 10 ? FWDS(2, 2) : FWDS(2, 4);
-                return var == 9 ? FWDS(3, 2) : FWDS(3, 1);
+                if (ndim == 2) return var == 10 ? FWDS(2, 3) : FWDS(2, 4);
+                return var == 10 ? FWDS(3, 2) : FWDS(3, 1);
 #undef FWDS
             }
             if (ndim == 2) {
-                if (!backward) return var == 5 ? FWD(2, 4) : var == 6 ? FWD(2, 5) : var == 7 ? FWD(2, 6) : FWD(2, 3);
-                return var == 5 ? BWD(2, 2, 4) : var == 6 ? BWD(2, 4, 3) : var == 7 ? BWD(2, 1, 5) : BWD(2, 4, 2);
+                if (!backward) return (var == 5 || var >= 9) ? FWD(2, 4) : var == 6 ? FWD(2, 5) : var == 7 ? FWD(2, 6) : FWD(2, 3);
+                return (var == 5 || var >= 9) ? BWD(2, 2, 4) : var == 6 ? BWD(2, 4, 3) : var == 7 ? BWD(2, 1, 5) : BWD(2, 4, 2);
             }
-            if (!backward) return var == 5 ? FWD(3, 3) : var == 6 ? FWD(3, 4) : var == 7 ? FWD(3, 2) : FWD(3, 5);
-            return var == 5 ? BWD(3, 1, 3) : var == 6 ? BWD(3, 2, 2) : var == 7 ? BWD(3, 1, 4) : BWD(3, 4, 1);
+            if (!backward) return (var == 5 || var >= 9) ? FWD(3, 3) : var == 6 ? FWD(3, 4) : var == 7 ? FWD(3, 2) : FWD(3, 5);
+            return (var == 5 || var >= 9) ? BWD(3, 1, 3) : var == 6 ? BWD(3, 2, 2) : var == 7 ? BWD(3, 1, 4) : BWD(3, 4, 1);
 #undef FWD
 #undef BWD
         }
     }
     const long z = (long)s.N * (ndim == 3 ? s.O[1] : 1);
     const unsigned gy = (unsigned)((s.O[ndim - 1] + TILE - 1) / TILE);
-    if (z > 65535 || gy > 65535) { set_error("interpolate: batch x middle extent %ld exceeds 65535", z); return kErrUnsupported; }
+    const int mid1 = ndim == 3 ? s.O[1] : 1;
+    if (gy > 65535 || mid1 > 65535) { set_error("interpolate: output extent exceeds the grid limits of the tile kernels"); return kErrUnsupported; }
+    if (z > 65535) {     // gridDim.z limit of the one-tile-per-CTA kernels: slab the batch (as the 1-D path does)
+        const int per = 65535 / mid1;
+        size_t in_plane = (size_t)s.C, out_plane = (size_t)s.C, pts = 1;
+        for (int j = 0; j < ndim; ++j) { in_plane *= s.S[j]; out_plane *= s.O[j]; pts *= s.O[j]; }
+        for (int n0 = 0; n0 < s.N; n0 += per) {
+            Shape sub = s;
+            sub.N = s.N - n0 < per ? s.N - n0 : per;
+            const size_t din = (size_t)n0 * in_plane, dout = (size_t)n0 * out_plane, dgr = (size_t)n0 * ndim * pts;
+            const int rc = interp_t<T>(backward, ndim, sub, (const T*)data + din, (const T*)grid + dgr,
+                                       gout ? (const T*)gout + dout : nullptr,
+                                       out_or_dgrid ? (T*)out_or_dgrid + (backward ? dgr : dout) : nullptr,
+                                       ddata ? (T*)ddata + din : nullptr, st);
+            if (rc != kOk) return rc;
+        }
+        return kOk;
+    }
     dim3 g((unsigned)((s.O[0] + TILE - 1) / TILE), gy, (unsigned)z);
     prof_begin(backward ? kProfInterpBwd : kProfInterpFwd, st);
     if (ndim == 2) {

@@ -6,6 +6,7 @@
 #pragma once
 
 #include "cpab_common.cuh"
+#include "cpab_f32x2.cuh"
 
 namespace cpab {
 
@@ -48,8 +49,8 @@ __device__ __forceinline__ void taps(T gcoord, int size, int& t0, int& t1, T& wg
 // x + 1.5*2^23 rounded DOWN is exactly 1.5*2^23 + floor(x) (ulp 1 in [2^23, 2^24)), so the integer
 // floor is a difference of bit patterns; x below -1 (and NaN: fmaxf returns the other operand) is
 // lifted to -1, which has the same clamped taps (0, 0); x >= 2^22 yields an integer >= 2^22 > size-1,
-// clamped to size-1 like the reference's floor.  The clamped lower tap goes back to float through
-// the same constant (exact), and the weight is formed from the unclamped x as the reference does.
+// clamped to size-1 like the reference's floor.  The clamped lower tap goes back to float exactly,
+// and the weight is formed from the unclamped x as the reference does.
 // Requires size <= 2^22 (kMaxInterpExtentF32; the launchers refuse larger float32 extents).
 // `t1 - t0` is 0 or 1.
 template <>
@@ -63,7 +64,7 @@ __device__ __forceinline__ void taps<float>(float gcoord, int size, int& t0, int
     const int i = __float_as_int(t) - 0x4B400000;           // floor(x), any int when |x| is huge
     t0 = min(max(i, 0), ihi);
     t1 = t0 + ((unsigned)i < (unsigned)ihi ? 1 : 0);        // clamp(i + 1) differs from t0 iff 0 <= i < size-1
-    wgt = __fsub_rn(x, __fsub_rn(__int_as_float(t0 + 0x4B400000), magic));
+    wgt = __fsub_rn(x, __int2float_rn(t0));                 // (0 <= t0 < 2^22: exact; I2FP runs on the ALU pipe)
 }
 
 // multilinear blend of 2^NDIM corner values, x first (bit 0), then y, then z
@@ -82,6 +83,36 @@ __device__ __forceinline__ T blend(const T* v, const T* w)
     }
     return a[0];
 }
+
+// float32, NDIM >= 2: the same separately rounded products and sums with the products packed
+// (FMUL2, cpab_f32x2.cuh): two outputs of a level share their weights, so (a[2m], a[2m+2]) * (1-w)
+// and (a[2m+1], a[2m+3]) * w are one instruction each; the last level multiplies (a0, a1) by
+// (1-w, w).  Sums stay scalar (ptxas would contract a packed product feeding a packed add into an
+// FFMA2).  Bit-identical to the scalar form; 8 instead of 11 instructions in 2-D, 17 instead of 24
+// in 3-D.
+template <int NDIM>
+__device__ __forceinline__ float blend_packed(const float* v, const float* w)
+{
+    static_assert(NDIM >= 2, "packed blend needs at least two levels");
+    float a[1 << NDIM];
+#pragma unroll
+    for (int i = 0; i < (1 << NDIM); ++i) a[i] = v[i];
+#pragma unroll
+    for (int j = 0; j < NDIM - 1; ++j) {
+        const float om = __fsub_rn(1.0f, w[j]);
+#pragma unroll
+        for (int m = 0; m < (1 << (NDIM - 1 - j)); m += 2) {
+            const F2 P = mul2(pk(a[2 * m], a[2 * m + 2]), bc(om));
+            const F2 Q = mul2(pk(a[2 * m + 1], a[2 * m + 3]), bc(w[j]));
+            a[m] = __fadd_rn(lo(P), lo(Q));
+            a[m + 1] = __fadd_rn(hi(P), hi(Q));
+        }
+    }
+    const F2 Rr = mul2(pk(a[0], a[1]), pk(__fsub_rn(1.0f, w[NDIM - 1]), w[NDIM - 1]));
+    return __fadd_rn(lo(Rr), hi(Rr));
+}
+template <> __device__ __forceinline__ float blend<2, float>(const float* v, const float* w) { return blend_packed<2>(v, w); }
+template <> __device__ __forceinline__ float blend<3, float>(const float* v, const float* w) { return blend_packed<3>(v, w); }
 
 // reverse of blend: corner weights gv[] (d out / d v) and dw[] (d out / d w_j), scaled by g
 template <int NDIM, typename T>

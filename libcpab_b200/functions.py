@@ -96,8 +96,18 @@ def sample_transformation(d, n_sample=1, mean=None, cov=None, device="cpu"):
     dev = _device(device)
     mean = torch.zeros(d, dtype=torch.float32, device=dev) if mean is None else mean
     cov = torch.eye(d, dtype=torch.float32, device=dev) if cov is None else cov
-    dist = torch.distributions.MultivariateNormal(mean, cov)
-    return dist.sample((n_sample,)).to(dev)
+    try:
+        dist = torch.distributions.MultivariateNormal(mean, cov)
+        return dist.sample((n_sample,)).to(dev)
+    except (ValueError, RuntimeError):
+        # A covariance that is positive SEMI-definite up to rounding (the smooth prior of
+        # Cpab.sample_transformation_with_prior in float32) has no Cholesky factor: sample through its
+        # eigen-decomposition instead, as numpy.random.multivariate_normal -- the reference's numpy
+        # backend, libcpab/numpy/functions.py:86-90 -- does.
+        w, V = torch.linalg.eigh(0.5 * (cov + cov.t()).double())
+        z = torch.randn(n_sample, d, dtype=torch.float64, device=cov.device)
+        out = mean.double() + (z * w.clamp_min(0).sqrt()) @ V.t()
+        return out.to(torch.float32).to(dev)
 
 
 def identity(d, n_sample=1, epsilon=0, device="cpu"):

@@ -68,6 +68,33 @@ def test_gradient_matches_differenced_checker(name):
     assert rel_err(dpts.cpu().numpy(), fdp) < 1e-5
 
 
+def test_gradient_at_the_identity_is_not_zero():
+    """theta = 0 (the usual identity initialisation): every velocity vanishes, every point is a fixed
+    point, and yet d x_f / d b = 1 and d x_f / d a = x.  The closed-form gradient there must equal the
+    fixed-step adjoint's (which is exact for a field that is zero) -- ADVICE r1."""
+    from libcpab_b200 import ops
+    g = load_golden("cfg1_1d50")
+    nc = g["nc"].tolist()
+    B = g["B"]
+    grid = g["grid"].astype(np.float64)
+    As = np.zeros((3, nc[0], 1, 2))
+    rng = np.random.default_rng(4)
+    gout = rng.normal(size=(3, 1, grid.shape[1]))
+    dth, dpts = ops.backward_theta_closed_form(dev(grid), dev(As), dev(B), dev(gout), nc, want_dpoints=True)
+    ref, _ = ops.backward_theta(dev(grid), dev(As), dev(B), dev(gout), nc, 50)
+    assert float(ref.abs().max()) > 1e-3
+    assert rel_err(dth.cpu().numpy(), ref.cpu().numpy()) < 1e-9
+    assert np.allclose(dpts.cpu().numpy(), gout)                          # d x_f / d x_0 = e^{a t} = 1
+    # a training step from T.identity() moves
+    from libcpab_b200 import Cpab
+    T = Cpab(nc, backend="pytorch", device="gpu", basis=B)
+    T.params.closed_form = True
+    theta = T.identity(2).requires_grad_(True)
+    out = T.transform_grid(T.uniform_meshgrid([64]), theta)
+    (out * torch.linspace(-1, 1, 64, device="cuda")).sum().backward()
+    assert float(theta.grad.abs().max()) > 1e-3
+
+
 def test_api_switch_and_flow_properties_at_full_size():
     """BASELINE configs[4] shape: 8192 series x 1024 points, tess [100]."""
     from libcpab_b200 import Cpab

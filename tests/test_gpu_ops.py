@@ -410,6 +410,26 @@ def test_interpolate_persistent_kernels_walk_many_tiles(shape, outsize, cap):
         _lib.set_tuning("interp_variant", 9)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_interpolate_batch_beyond_the_grid_z_limit(dtype):
+    """More than 65535 samples through the one-tile-per-CTA kernels (float64, and float32 with an
+    output extent the 16-byte path does not take): the batch is slabbed, as the reference has no limit."""
+    from libcpab_b200 import ops
+    rng = np.random.default_rng(9)
+    N, outsize = 66000, (5, 3)
+    data = rng.uniform(size=(N, 1, 4, 3)).astype(dtype)
+    grid = rng.uniform(-0.1, 1.1, (N, 2, 15)).astype(dtype)
+    out = ops.interpolate_forward(dev(data), dev(grid), outsize).cpu().numpy()
+    sel = np.r_[0:50, 65500:65600, N - 50:N]
+    assert np.array_equal(out[sel], O.interpolate(data[sel], grid[sel], outsize))
+    gout = rng.normal(size=out.shape).astype(dtype)
+    dgrid, ddata = ops.interpolate_backward(dev(data), dev(grid), dev(gout), True, True)
+    dg_o, dd_o = O.interpolate_vjp(data[sel], grid[sel], outsize, gout[sel])
+    tol = F32_TOL if dtype == np.float32 else 1e-12
+    assert rel_err(dgrid.cpu().numpy()[sel], dg_o) < tol
+    assert rel_err(ddata.cpu().numpy()[sel], dd_o) < tol
+
+
 def test_interpolate_taps_extreme_coordinates():
     """The conversion-free tap arithmetic (cpab_sample.cuh) against the oracle on coordinates far
     outside the image, exactly on texels, just below them, negative zero, and huge (below 2^63 after

@@ -100,6 +100,11 @@ def test_reference_cpab_transform_data(name):
     (out * cuda(g["data_gout"])).sum().backward()
     e_th = rel_err(theta.grad.cpu().numpy(), g["data_dtheta"])
     e_dd = rel_err(data.grad.cpu().numpy(), g["data_ddata"])
-    print("reference transform_data on libcpab_b200 %s: max |out - ref| %.3g, dtheta %.3g, ddata %.3g" % (name, err.max(), e_th, e_dd))
-    assert err.max() < 1e-4 and np.median(err) < 1e-6
+    # the sampled image moves by (point error) x (steepest texel slope); the points agree to
+    # 2e-5 x flow gain (previous test: torch's expm on the GPU rounds differently from the CPU's)
+    slope = max(s - 1 for s in g["data"].shape[2:]) * np.abs(np.diff(g["data"], axis=-1)).max() * len(outsize)
+    bound = 2 * TOL * flow_gain(g["As"]) * slope + 1e-6
+    print("reference transform_data on libcpab_b200 %s: max |out - ref| %.3g (bound %.3g), median %.3g, dtheta %.3g, ddata %.3g"
+          % (name, err.max(), bound, np.median(err), e_th, e_dd))
+    assert err.max() < bound and np.median(err) < 2e-6
     assert e_th < 2e-3 and e_dd < 2e-3
