@@ -148,7 +148,11 @@ inline Geom make_geom(int ndim, const int* nc)
         const float gap = (g.top3[j] - c) * g.nf[j];
         if (gap > edge3) edge3 = gap;
     }
-    g.band3 = 4e-6f + 3.0f * edge3;
+    // + the (q - 0.5) + 0.5 round trip of the reference's push: up to 2^-25 per coordinate, three
+    // coordinates per plane, in local units
+    float nmax = 1.0f;
+    for (int j = 0; j < 3; ++j) nmax = fmaxf(nmax, g.nf[j]);
+    g.band3 = 4e-6f + 3.0f * edge3 + 3.0f * 2.9802322e-08f * nmax;
     return g;
 }
 
@@ -485,24 +489,39 @@ CPAB_HD_NOINLINE int find_cell_3d_full(float p0, float p1, float p2, const Geom&
     return cell;
 }
 
-// Lean 3-D fast path (the 2-D scheme on three axes).  Handles ONLY points with every coordinate in
-// [0, top]: no outside-the-box push, no lower clamp; the reference's upper clamp and its
-// `mymin(n-1, .)` are reproduced by min(k, n-1) (a coordinate of exactly 1.0 keeps local
-// coordinate 0 in the last cube -- the reference's own quirk).  One-sided column
-// estimates as in divmod_up (x, y packed, z scalar): floor(c * nup) is the exact column or one
-// more, r = fma(-k, w, c) is exact and negative exactly in the second case.  Parity swap, the four
-// separating planes in the reference's order; since the corner tetrahedra are disjoint, outside
-// the guard band at most one of t1..t4 is non-negative and the index is 10 - sum_i i*sign(t_i).
-// Returns true when the point needs find_cell_3d_full instead: a coordinate outside [0, top] (or
-// NaN), an estimate one too large, or a point within the band of a plane.  ~50 instructions against
-// ~100 of find_cell_3d_fast_t.  NEAR: also the certificate's `dist` (see find_cell_near).
+// Lean 3-D fast path (the 2-D scheme on three axes).
+//   * Coordinates are clamped to [0, ctop].  This IS the reference's treatment of a point with at
+//     most ONE coordinate outside [0, 1] (cpab_ops.cpp:119-141): if that coordinate is x or y, its
+//     outside-the-box push only moves it onto the face (the `half*inc` shifts need two coordinates
+//     outside; a z outside as well would be pushed too, to a different place than the later clamp
+//     with the reference's z bound nz*inc_x - 1e-8 puts it); if it is z, there is no push and the
+//     clamp to [0, n*inc - 1e-8] acts alone.  The push also sends the other coordinates through
+//     (q - 0.5) + 0.5, which can move them by 2^-25: the guard band of the plane tests covers that
+//     (band3).  Zero-boundary flows park points on the faces, where they wobble an ulp outside on
+//     many steps -- this case has to stay on the fast path.  A point with x AND y outside
+//     (|q - 0.5| > 0.5 in the reference's own rounded arithmetic), or with x or y on/over a face
+//     and z outside, leaves.
+//   * The reference's `mymin(n-1, .)` is min(k, n-1): a coordinate of exactly 1.0 keeps local
+//     coordinate 0 in the last cube (the reference's own quirk).
+//   * One-sided column estimates as in divmod_up (x, y packed, z scalar): floor(c * nup) is the exact
+//     column or one more, r = fma(-k, w, c) is exact and negative exactly in the second case (leaves).
+//   * Parity swap, then the four separating planes in the reference's order; the corner tetrahedra
+//     are disjoint, so outside the guard band at most one of t1..t4 is non-negative and the index
+//     is 10 - sum_i i * signbit(t_i).
+// Returns true when the point needs find_cell_3d_full instead.  ~55 instructions against ~100 of
+// find_cell_3d_fast_t.  The cell index is in range even then.  NEAR: also the certificate's `dist`
+// (see find_cell_near); -1 where the lean path does not apply.
 template <bool NEAR>
 CPAB_HD bool find_cell_3d_lean(float q0, float q1, float q2, const Geom& g, float magic, int& cell, float& dist)
 {
-    const float lo = fminf(fminf(q0, q1), q2);
-    const float hi = fminf(fminf(g.top3[0] - q0, g.top3[1] - q1), g.top3[2] - q2);
-    // (ctop3 == top3 where no clamp is needed: unconditional, a data-dependent select would cost more)
-    const float c0 = fminf(q0, g.ctop3[0]), c1 = fminf(q1, g.ctop3[1]), c2 = fminf(q2, g.ctop3[2]);
+    // the reference's ax, ay, az (same rounding); "outside" is |q - 0.5| > 0.5
+    const float dx = fabsf(q0 - 0.5f), dy = fabsf(q1 - 0.5f), dz = fabsf(q2 - 0.5f);
+    // the push is ENTERED on the exact tests x, y < 0 or > 1 (superset: max(dx, dy) >= 0.5, which also
+    // catches a coordinate like -1e-9 whose dx rounds to 0.5); once entered it also moves a z with
+    // dz > 0.5 onto its face, which the later clamp (bound nz*inc_x - 1e-8, possibly > 1) would not
+    const bool out2 = (fminf(dx, dy) > 0.5f) | ((fmaxf(dx, dy) >= 0.5f) & (dz > 0.5f));
+    const float c0 = fminf(fmaxf(q0, 0.0f), g.ctop3[0]), c1 = fminf(fmaxf(q1, 0.0f), g.ctop3[1]);
+    const float c2 = fminf(fmaxf(q2, 0.0f), g.ctop3[2]);
     float kx, ky, kz, rx, ry, rz, x, y, z;
 #if defined(__CUDA_ARCH__)
     {
@@ -540,10 +559,10 @@ CPAB_HD bool find_cell_3d_lean(float q0, float q1, float q2, const Geom& g, floa
     const int tet = (t1 >= 0.0f ? 1 : 0) + (t2 >= 0.0f ? 2 : 0) + (t3 >= 0.0f ? 3 : 0) + (t4 >= 0.0f ? 4 : 0);
 #endif
     cell = 5 * cube + tet;
-    // (negated >=: a NaN coordinate makes `nearest` NaN -- every plane involves all three -- and must leave)
-    const bool rare = !(fminf(fminf(lo, hi), rmin) >= 0.0f) | !(nearest >= g.band3);
+    const bool rare = out2 | !(rmin >= 0.0f) | !(nearest >= g.band3);
     if (NEAR) {
         const float lo3 = fminf(fminf(x, y), z), hi3 = fmaxf(fmaxf(x, y), z);
+        // a clamped coordinate sits on a face (local coordinate 0 or next to 1): dist ~ 0, never certified
         dist = rare ? -1.0f : fminf(nearest, fminf(lo3, 1.0f - hi3));
     }
     return rare;

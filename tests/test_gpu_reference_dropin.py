@@ -106,5 +106,6 @@ def test_reference_cpab_transform_data(name):
     bound = 2 * TOL * flow_gain(g["As"]) * slope + 1e-6
     print("reference transform_data on libcpab_b200 %s: max |out - ref| %.3g (bound %.3g), median %.3g, dtheta %.3g, ddata %.3g"
           % (name, err.max(), bound, np.median(err), e_th, e_dd))
-    assert err.max() < bound and np.median(err) < 2e-6
+    mslope = max(s - 1 for s in g["data"].shape[2:]) * np.abs(np.diff(g["data"], axis=-1)).mean() * len(outsize)
+    assert err.max() < bound and np.median(err) < 2 * TOL * flow_gain(g["As"]) * mslope + 1e-6
     assert e_th < 2e-3 and e_dd < 2e-3

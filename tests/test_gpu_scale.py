@@ -134,7 +134,8 @@ def test_point_sharded_equals_unsharded(tess, n_theta, outsize, ws):
             (out * Rfull[..., lo:hi]).sum().backward()
             gsum += t.grad
     assert bool((torch.cat(parts, dim=-1) == full).all())
-    assert rel_err(gsum.cpu().numpy(), th.grad.cpu().numpy()) < 1e-6
+    # (float32 sums in a different order: per-slab atomics, then the sum over slabs)
+    assert rel_err(gsum.cpu().numpy(), th.grad.cpu().numpy()) < 3e-6
 
 
 def test_point_sharded_nccl_two_gpus(tmp_path):
@@ -179,4 +180,4 @@ dist.destroy_process_group()
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
-    assert float(line[1]) < 1e-6 and line[2] == "True"
+    assert float(line[1]) < 3e-6 and line[2] == "True"
