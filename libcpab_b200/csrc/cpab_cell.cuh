@@ -60,6 +60,7 @@ struct Geom {
     float ctop3[3];     // 3-D lean path: largest coordinate at which the one-sided estimate is still cell n-1
     float band3;        // 3-D: guard band of the separating-plane tests
     int clamp3;         // 3-D lean path: ctop3 < top3 on some axis (the estimate needs the clamp)
+    int zpush3;         // 3-D lean path: the reference's z bound nz*inc_x - 1e-8 exceeds 1 (push != clamp for z)
     // ---- float64 check mode -------------------------------------------------------------------
     double wd[3];       // 1.0 / n
     double spand[3];    // n * wd
@@ -153,6 +154,7 @@ inline Geom make_geom(int ndim, const int* nc)
     float nmax = 1.0f;
     for (int j = 0; j < 3; ++j) nmax = fmaxf(nmax, g.nf[j]);
     g.band3 = 4e-6f + 3.0f * edge3 + 3.0f * 2.9802322e-08f * nmax;
+    g.zpush3 = g.hi3[2] > 1.0f ? 1 : 0;
     return g;
 }
 
@@ -498,9 +500,10 @@ CPAB_HD_NOINLINE int find_cell_3d_full(float p0, float p1, float p2, const Geom&
 //     clamp to [0, n*inc - 1e-8] acts alone.  The push also sends the other coordinates through
 //     (q - 0.5) + 0.5, which can move them by 2^-25: the guard band of the plane tests covers that
 //     (band3).  Zero-boundary flows park points on the faces, where they wobble an ulp outside on
-//     many steps -- this case has to stay on the fast path.  A point with x AND y outside
-//     (|q - 0.5| > 0.5 in the reference's own rounded arithmetic), or with x or y on/over a face
-//     and z outside, leaves.
+//     many steps -- edge and corner points on two or three faces at once -- and all of this has
+//     to stay on the fast path.  Only a point with all three coordinates outside (a `half*inc`
+//     shift may apply), or -- in tessellations whose z bound exceeds 1 -- with x or y outside and
+//     z outside, leaves.
 //   * The reference's `mymin(n-1, .)` is min(k, n-1): a coordinate of exactly 1.0 keeps local
 //     coordinate 0 in the last cube (the reference's own quirk).
 //   * One-sided column estimates as in divmod_up (x, y packed, z scalar): floor(c * nup) is the exact
@@ -514,14 +517,18 @@ CPAB_HD_NOINLINE int find_cell_3d_full(float p0, float p1, float p2, const Geom&
 template <bool NEAR>
 CPAB_HD bool find_cell_3d_lean(float q0, float q1, float q2, const Geom& g, float magic, int& cell, float& dist)
 {
-    // the reference's ax, ay, az (same rounding); "outside" is |q - 0.5| > 0.5
+    // the reference's ax, ay, az (same rounding); a coordinate is pushed when |q - 0.5| > 0.5
     const float dx = fabsf(q0 - 0.5f), dy = fabsf(q1 - 0.5f), dz = fabsf(q2 - 0.5f);
-    // the push is ENTERED on the exact tests x, y < 0 or > 1 (superset: max(dx, dy) >= 0.5, which also
-    // catches a coordinate like -1e-9 whose dx rounds to 0.5); once entered it also moves a z with
-    // dz > 0.5 onto its face, which the later clamp (bound nz*inc_x - 1e-8, possibly > 1) would not
-    const bool out2 = (fminf(dx, dy) > 0.5f) | ((fmaxf(dx, dy) >= 0.5f) & (dz > 0.5f));
     const float c0 = fminf(fmaxf(q0, 0.0f), g.ctop3[0]), c1 = fminf(fmaxf(q1, 0.0f), g.ctop3[1]);
     const float c2 = fminf(fmaxf(q2, 0.0f), g.ctop3[2]);
+    // When does the push differ from these clamps?  (1) All three coordinates outside: only then a
+    // `half*inc` shift applies (each shift needs its coordinate to be the smallest of three |q - 0.5|
+    // AND above 0.5) -- the eight corner regions.  (2) Tessellations whose z bound nz*inc_x - 1e-8
+    // exceeds 1 (g.zpush3): the push, ENTERED on the exact tests x, y < 0 or > 1, moves a z with
+    // dz > 0.5 onto its face where the clamp alone would leave it in (1, bound].  `c != q` is that
+    // exact test (or a superset where ctop < 1).
+    const bool out2 = (fminf(fminf(dx, dy), dz) > 0.5f) |
+                      ((g.zpush3 != 0) & ((c0 != q0) | (c1 != q1)) & (dz > 0.5f));
     float kx, ky, kz, rx, ry, rz, x, y, z;
 #if defined(__CUDA_ARCH__)
     {
@@ -568,11 +575,46 @@ CPAB_HD bool find_cell_3d_lean(float q0, float q1, float q2, const Geom& g, floa
     return rare;
 }
 
+// Slow step of the integration loops (out of line, behind the warp vote).  The common reason to be
+// here is a point within the guard band of a separating plane -- a uniform_meshgrid commensurate
+// with the tessellation puts ~3 % of its points EXACTLY on such planes at t = 0 -- with everything
+// else in order: for those the exact remainders of the one-sided estimate are the reference's
+// fmod results, and only its double divisions and plane tests (cpab_ops.cpp:143-182) remain to be
+// replayed (~150 instructions instead of ~500 for the complete search).
+CPAB_HD_NOINLINE int find_cell_3d_slow(float q0, float q1, float q2, const Geom& g, float magic)
+{
+    const float dx = fabsf(q0 - 0.5f), dy = fabsf(q1 - 0.5f), dz = fabsf(q2 - 0.5f);
+    const float c0 = fminf(fmaxf(q0, 0.0f), g.top3[0]), c1 = fminf(fmaxf(q1, 0.0f), g.top3[1]);
+    const float c2 = fminf(fmaxf(q2, 0.0f), g.top3[2]);
+    const bool out2 = (fminf(fminf(dx, dy), dz) > 0.5f) |
+                      ((g.zpush3 != 0) & ((c0 != q0) | (c1 != q1)) & (dz > 0.5f));
+    // (clamped to top3 here, not ctop3: the reference's own value; beyond ctop3 the estimate may be off)
+    const bool beyond = (c0 > g.ctop3[0]) | (c1 > g.ctop3[1]) | (c2 > g.ctop3[2]);
+    float kx, ky, kz, rx, ry, rz;
+    divmod_up(c0, g.nup[0], g.w[0], magic, kx, rx);
+    divmod_up(c1, g.nup[1], g.w[1], magic, ky, ry);
+    divmod_up(c2, g.nup[2], g.w[2], magic, kz, rz);
+    // (a point that enters the reference's push -- x or y outside, exact tests -- has all three
+    //  coordinates sent through (q - 0.5) + 0.5, which matters inside the band: complete search)
+    const bool entered = (q0 < 0.0f) | (q0 > 1.0f) | (q1 < 0.0f) | (q1 > 1.0f);
+    if (out2 | beyond | entered | !(fminf(fminf(rx, ry), rz) >= 0.0f)) return find_cell_3d_full(q0, q1, q2, g);
+    const int i = (int)fminf(kx, g.nm1[0]), j = (int)fminf(ky, g.nm1[1]), k = (int)fminf(kz, g.nm1[2]);
+    int cell = 5 * (i + j * g.nc[0] + k * g.nc[0] * g.nc[1]);
+    double x = (double)rx / (double)g.w[0], y = (double)ry / (double)g.w[1];
+    const double z = (double)rz / (double)g.w[2];
+    if ((i + j + k) & 1) { const double t = x; x = y; y = 1 - t; }
+    if (-x - y + z >= 0) cell += 1;
+    else if (x + y + z - 2 >= 0) cell += 2;
+    else if (-x + y - z >= 0) cell += 3;
+    else if (x - y - z >= 0) cell += 4;
+    return cell;
+}
+
 CPAB_HD int find_cell_3d(float p0, float p1, float p2, const Geom& g, float magic = 12582912.0f)
 {
     int cell;
     float dist;
-    if (find_cell_3d_lean<false>(p0, p1, p2, g, magic, cell, dist)) return find_cell_3d_full(p0, p1, p2, g);
+    if (find_cell_3d_lean<false>(p0, p1, p2, g, magic, cell, dist)) return find_cell_3d_slow(p0, p1, p2, g, magic);
     return cell;
 }
 
@@ -707,7 +749,7 @@ template <int NDIM> CPAB_HD bool find_cell_try(const float* p, const Geom& g, fl
 template <int NDIM> CPAB_HD int find_cell_finish(const float* p, const Geom& g, const CellEst& est)
 {
     if (NDIM == 2) return find_cell_2d_rare(p[0], p[1], est.kx, est.rx, est.ky, est.ry, g);
-    if (NDIM == 3) return find_cell_3d_full(p[0], p[1], p[2], g);
+    if (NDIM == 3) return find_cell_3d_slow(p[0], p[1], p[2], g, 12582912.0f);
     return find_cell<NDIM, float>(p, g);
 }
 template <int NDIM> CPAB_HD bool find_cell_try(const double* p, const Geom& g, float, int& cell, CellEst&)
