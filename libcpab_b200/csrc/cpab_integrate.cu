@@ -49,7 +49,13 @@
 #endif
 
 
+#ifndef CPAB_FWD_UNROLL
+#define CPAB_FWD_UNROLL 2      // steps per trip of k_forward's inner loop (measured: profiles/r02_forward_unroll.txt)
+#endif
+
 namespace cpab {
+
+constexpr int kFwdUnroll = CPAB_FWD_UNROLL;
 
 // =====================================================================================================
 // findcellidx
@@ -174,7 +180,7 @@ k_forward(const T* __restrict__ points, const T* __restrict__ trels, T* __restri
             int c[PPT];
             bool rare[PPT];
             CellEst est[PPT];
-#pragma unroll 2
+#pragma unroll kFwdUnroll
             for (; s < nsteps; ++s) {
                 bool any = false;
 #pragma unroll
@@ -328,7 +334,7 @@ int set_tuning(const char* key, int value)
     if (k == "bwd_seg" && (value == 0 || value == 3 || value == 5 || value == 10)) { t.bwd_seg = value; return kOk; }
     if (k == "bwd_stage" && value >= -1 && value <= 1) { t.bwd_stage = value; return kOk; }
     if (k == "bwd_block" && (value == 64 || value == 128 || value == 256)) { t.bwd_block = value; return kOk; }
-    if (k == "interp_variant" && value >= 0 && value <= 14) { set_interp_variant(value); return kOk; }
+    if (k == "interp_variant" && value >= 0 && value <= 15) { set_interp_variant(value); return kOk; }
     if (k == "interp_max_ctas" && value >= 0) { set_interp_max_ctas(value); return kOk; }
     set_error("unknown tuning key/value %s=%d", key, value);
     return kErrArgument;

@@ -462,15 +462,15 @@ k_interp_fwd_pipe(const float* __restrict__ data, const float* __restrict__ grid
     int stage = 0;
     for (; cur.n < s.N; cur.advance(tg)) {
         cp_async_wait<1>();
-        __syncthreads();
+        if (PROBE == 4) __syncwarp(); else __syncthreads();       // (probe 4: timing only, results are wrong)
         const int nxt = stage >= 1 ? stage - 1 : kStages - 1;      // (stage + 2) % 3
         pf.advance(tg);
         prefetch_grid_tile<NDIM>(grid, s, pf, ring + 4u * (uint32_t)(nxt * STAGE));
         const TilePos tp = cur.pos();
         const bool full = (tp.a0 + TILE <= s.O[0]) && (tp.f0 + TILE <= s.O[NDIM - 1]);
         const uint32_t sg = ring + 4u * (uint32_t)(stage * STAGE);
-        if (full) interp_fwd_compute<NDIM, true, ONECH, PROBE>(data, out, s, tp, sg);
-        else interp_fwd_compute<NDIM, false, ONECH, PROBE>(data, out, s, tp, sg);
+        if (full) interp_fwd_compute<NDIM, true, ONECH, PROBE == 4 ? 0 : PROBE>(data, out, s, tp, sg);
+        else interp_fwd_compute<NDIM, false, ONECH, PROBE == 4 ? 0 : PROBE>(data, out, s, tp, sg);
         stage = stage + 1 == kStages ? 0 : stage + 1;
     }
     cp_async_wait<0>();
@@ -941,11 +941,13 @@ int interp_t(bool backward, int ndim, const Shape& s, const void* data, const vo
             if (!backward && s.C == 1 && ndim == 2 && var >= 12) {      // measurement probes (see interp_fwd_compute)
                 if (var == 12) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 1>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
                 if (var == 13) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 2>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
+                if (var == 15) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 4>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
                 return launch_pipe(k_interp_fwd_pipe<2, 4, true, 3>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
             }
             if (!backward && s.C == 1 && ndim == 2 && var >= 12) {      // measurement probes (see interp_fwd_compute)
                 if (var == 12) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 1>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
                 if (var == 13) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 2>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
+                if (var == 15) return launch_pipe(k_interp_fwd_pipe<2, 4, true, 4>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
                 return launch_pipe(k_interp_fwd_pipe<2, 4, true, 3>, ndim, s, st, kProfInterpFwd, 0, d, gr, o);
             }
             // 9-11: backward (single channel, d/dgrid only) with the register software pipeline; forward:

@@ -23,7 +23,7 @@ for tess, n, size, kw in cases:
     with torch.no_grad(): gt = T.transform_grid(grid, theta)
     data = torch.rand(n, 1, *size, device='cuda'); g2 = torch.randn_like(data)
     nd = len(tess); pts = n * int(np.prod(size))
-    for var in (2, 5, 9, 10, 11, 12, 13, 14):
+    for var in (2, 5, 9, 10, 11, 12, 13, 14, 15):
         _lib.set_tuning("interp_variant", var)
         ms = timeit(lambda: ops.interpolate_forward(data, gt, size))
         _lib.profile_enable(True)           # the same launches timed by the library's own event pairs (what bench.py reads)
