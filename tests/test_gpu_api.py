@@ -61,10 +61,19 @@ def test_transform_grid_and_theta_gradient(name):
     keep = interior(g)
     assert rel_err(got[:, :, keep], g["grid_t"][:, :, keep]) < 2 * TOL * gain
     (out * cuda(g["gout"])).sum().backward()
-    # gradient: op-level parity (same As) is held to 1e-5 in test_gpu_ops; here As carries the
-    # GPU's own 1e-7 projection rounding and, in 3-D, the discontinuous face points
-    gtol = 2 * TOL * gain if len(nc) < 3 else 5e-3
-    assert rel_err(theta.grad.cpu().numpy(), g["dtheta"]) < gtol
+    got_g = theta.grad.cpu().numpy()
+    # gradient, kernel error: against the ORACLE's gradient for the As the GPU itself produced
+    # (identical inputs) -- the 1e-5 contract, on every theta
+    from conftest import assert_grad_parity, bs_of
+    ref_same_inputs = O.theta_grad(g["grid"], As.cpu().numpy(), bs_of(g["B"], nc), g["gout"], nc, 50, threads=8)
+    assert_grad_parity(got_g, ref_same_inputs, TOL, what="API %s, oracle on the GPU's own As" % name)
+    # gradient, end to end against the reference's own output: the RK2 sensitivity depends on theta
+    # through As only (not through Trels), and the GPU's projection reproduces the reference's As bit
+    # for bit on these fixtures, so the 1e-5 contract holds end to end as well (achieved: <= 2.8e-6)
+    e2e = rel_err(got_g, g["dtheta"])
+    print("API %s: dtheta end to end vs the reference %.3g; As max|diff| %.3g"
+          % (name, e2e, np.abs(As.cpu().numpy() - g["As"]).max()))
+    assert e2e < TOL
 
 
 @pytest.mark.parametrize("name", [n for n in golden_cases() if "data" in load_golden(n).files])
@@ -92,10 +101,27 @@ def test_transform_data_forward_backward(name):
     else:
         assert np.median(err) < 1e-5       # face points excepted (discontinuous reference field)
     (out * cuda(g["data_gout"])).sum().backward()
-    # d(out)/d(grid) is piecewise constant in the sample position: a point that lands on the
-    # other side of a texel boundary switches slope, so this gradient is texel-aware
-    assert rel_err(theta.grad.cpu().numpy(), g["data_dtheta"]) < (2e-3 if len(outsize) < 3 else 2e-2)
-    assert rel_err(data.grad.cpu().numpy(), g["data_ddata"]) < (2e-3 if len(outsize) < 3 else 2e-2)
+    # kernel error: against the oracle's VJP chain on the API's OWN transformed grid and As (identical
+    # inputs): d/d(data) and d/d(theta) to 1e-5
+    from conftest import assert_grad_parity, bs_of
+    from libcpab_b200 import ops
+    from libcpab_b200.transformer import _basis
+    nc = g["nc"].tolist()
+    B, Bt = _basis(T.params, theta.device, theta.dtype)
+    As_gpu, _ = ops.theta_to_trels(theta.detach(), Bt, nc, 50)
+    dgrid_o, ddata_o = O.interpolate_vjp(g["data"], grid_t.cpu().numpy(), outsize, g["data_gout"])
+    assert rel_err(data.grad.cpu().numpy(), ddata_o) < TOL
+    ref_same_inputs = O.theta_grad(O.uniform_meshgrid(outsize).astype(np.float32), As_gpu.cpu().numpy(),
+                                   bs_of(g["B"], nc), dgrid_o, nc, 50, threads=8)
+    assert_grad_parity(theta.grad.cpu().numpy(), ref_same_inputs, TOL, what="API transform_data %s, oracle on the GPU's own grid_t / As" % name)
+    # end to end against the reference's output: d(out)/d(grid) is piecewise constant in the sample
+    # position, so a point that the 1-ulp-different Trels put on the other side of a texel boundary
+    # switches slope -- inherent to comparing two float32 pipelines, not kernel error
+    e_th = rel_err(theta.grad.cpu().numpy(), g["data_dtheta"])
+    e_dd = rel_err(data.grad.cpu().numpy(), g["data_ddata"])
+    print("API transform_data %s: end to end vs the reference: dtheta %.3g, ddata %.3g" % (name, e_th, e_dd))
+    assert e_th < (2e-3 if len(outsize) < 3 else 2e-2)
+    assert e_dd < (2e-3 if len(outsize) < 3 else 2e-2)
 
 
 def test_interpolate_api_matches_reference():
