@@ -24,8 +24,8 @@ namespace cpab {
 
 namespace {
 
-int g_interp_max_ctas = 0;  // tests: cap the persistent grid so that every CTA walks over many tiles ("interp_max_ctas")
-int g_interp_variant = 9;   // 0-4: one tile per CTA (0: 4 points in flight, 1 CTA/SM target; 1: 2 / 6; 2: 1 / 8); 5-8: persistent kernels, grid tiles prefetched; 9-11: + texel loads software-pipelined in registers (single channel; default 9); 12-14: measurement probes (cpab_b200_set_tuning "interp_variant")
+thread_local int g_interp_max_ctas = 0;  // (per thread, like the other tuning knobs) tests: cap the persistent grid so that every CTA walks over many tiles ("interp_max_ctas")
+thread_local int g_interp_variant = 9;   // 0-4: one tile per CTA (0: 4 points in flight, 1 CTA/SM target; 1: 2 / 6; 2: 1 / 8); 5-8: persistent kernels, grid tiles prefetched; 9 (default): the same, backward with its loads software-pipelined in registers (single channel); 10-11: forward software-pipelined as well; 12-15: measurement probes (cpab_b200_set_tuning "interp_variant")
 
 // ---------------------------------------------------------------------------------------------
 // forward.  NDIM >= 2: CTA = 256 threads, tile 32 (first index) x 32 (last index);
