@@ -12,13 +12,12 @@
  *   - All data pointers are DEVICE pointers to contiguous row-major arrays of `dtype`
  *     (CPAB_F32 = float, CPAB_F64 = double "check mode") on the current device.
  *   - Every entry point is safe under CUDA-graph stream capture (no host synchronisation
- *     or allocation).  The only state inside the library is a 2 KB ring of self-resetting
- *     work counters in module memory, from which the adjoint kernel draws its work units; a launch
- *     takes the next of 256 slots, so up to 256 launches may be in flight on different streams
- *     (a captured graph keeps its slot: do not replay one graph concurrently with itself).
+ *     or allocation).  The work counters of the persistent kernels and the scratch of the gradient's
+ *     cell-sequence certificate live in the CALLER's workspace (zeroed by the first kernel of the
+ *     same launch sequence): nothing is shared between launches, streams or captured graphs.
  *   - The caller owns every buffer (outputs and workspace included); the library allocates no
- *     persistent memory and keeps no state besides the per-thread error string and the tuning
- *     knobs set through cpab_b200_set_tuning.
+ *     persistent memory and keeps no state besides the per-thread error string, the per-thread
+ *     tuning knobs set through cpab_b200_set_tuning and the (off by default) profiling accumulators.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
  *     enqueued on it and the call returns without synchronising.
  *   - `nc` points to `ndim` host ints (tessellation size per dimension), ndim in {1,2,3}.
@@ -67,8 +66,10 @@ const char* cpab_b200_last_error(void);
 /* Compile-time facts: "sm_100a;cuda=12.9;..." */
 const char* cpab_b200_build_info(void);
 
-/* Experiment knobs ("fwd_ppt", "chunk_pts", "bwd_seg", "bwd_block"); results never depend on them
- * beyond floating-point summation order in the gradient. */
+/* Experiment knobs, per calling thread ("fwd_ppt", "chunk_pts", "chunk_auto", "bwd_seg", "bwd_stage",
+ * "bwd_block", "interp_variant" 0-11, "interp_max_ctas"); results never depend on them beyond
+ * floating-point summation order in the gradient.  ("interp_variant" 12-15 are measurement probes of
+ * the interpolate forward that deliberately skip work: tools/interp_variants.py only.) */
 int cpab_b200_set_tuning(const char* key, int value);
 
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
