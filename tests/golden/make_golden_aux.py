@@ -63,5 +63,27 @@ def main():
         print(name, "v", tuple(v.shape), "cov", tuple(rec["cov"].shape), "sampled" if s is not None else "not sampled")
 
 
+def aligner_case():
+    """`CpabAligner.alignment_by_gradient` (libcpab/alignment.py:60-87): five Adam steps on a smooth
+    2-D image pair, by the unmodified reference on the CPU."""
+    import torch
+    from libcpab import Cpab, CpabAligner
+    torch.manual_seed(77)
+    T = Cpab([2, 2], backend="pytorch", device="cpu", zero_boundary=True, volume_perservation=False, override=True)
+    xs = torch.linspace(0, 1, 28)
+    x1 = (torch.sin(5.0 * xs)[:, None] * torch.cos(3.0 * xs)[None, :] + 0.3 * xs[:, None])[None, None].contiguous()
+    theta_true = 0.4 * T.sample_transformation(1)
+    x2 = T.transform_data(x1, theta_true, outsize=(28, 28)).detach()
+    A = CpabAligner(T)
+    theta = A.alignment_by_gradient(x1, x2, maxiter=5, lr=1e-2)
+    loss_end = float(torch.norm(T.transform_data(x1, theta.detach(), outsize=(28, 28)) - x2))
+    np.savez_compressed(os.path.join(OUT, "aux_align_2d.npz"), B=np.asarray(T.params.basis, dtype=np.float64),
+                        nc=np.asarray([2, 2], dtype=np.int32), x1=x1.numpy(), x2=x2.numpy(),
+                        theta_true=theta_true.numpy(), theta_out=theta.detach().numpy(),
+                        loss_start=np.float64(float(torch.norm(x1 - x2))), loss_end=np.float64(loss_end))
+    print("aux_align_2d", theta.detach().numpy().ravel()[:4], "loss", float(torch.norm(x1 - x2)), "->", loss_end)
+
+
 if __name__ == "__main__":
     main()
+    aligner_case()

@@ -275,3 +275,22 @@ def test_calc_vectorfield_and_prior_match_reference(name):
     print("%s: vectorfield rel err %.3g, prior covariance rel err %.3g" % (name, e_v, e_c))
     assert e_v < 2e-5      # zero-boundary fields cancel (|a x|, |b| >> |a x + b|): float32 evaluation order
     assert e_c < 1e-5
+
+
+def test_aligner_matches_the_reference_aligner():
+    """Five Adam steps of `CpabAligner.alignment_by_gradient` (libcpab/alignment.py:60-87) against the
+    theta the unmodified reference reached on the CPU (tests/golden/make_golden_aux.py)."""
+    from libcpab_b200 import Cpab, CpabAligner
+    g = load_golden("aux_align_2d")
+    T = Cpab(g["nc"].tolist(), backend="pytorch", device="gpu", basis=g["B"])
+    A = CpabAligner(T)
+    theta = A.alignment_by_gradient(cuda(g["x1"]), cuda(g["x2"]), maxiter=5, lr=1e-2)
+    err = float(np.abs(theta.detach().cpu().numpy() - g["theta_out"]).max())
+    loss_end = float(torch.norm(T.transform_data(cuda(g["x1"]), theta.detach(), outsize=(28, 28)) - cuda(g["x2"])))
+    print("aligner: max |theta - reference theta| %.3g (|theta| ~ %.3g); loss %.6f -> %.6f (reference: %.6f -> %.6f)"
+          % (err, float(np.abs(g["theta_out"]).max()), float(A.losses[0]), loss_end, float(g["loss_start"]), float(g["loss_end"])))
+    # (Adam divides by the running gradient magnitude: last-bit differences of the first gradients --
+    #  torch's own norm / interpolation on the GPU vs on the CPU included -- show at the 1e-4 level;
+    #  the reference's own aligner on the GPU differs from itself on the CPU by 7e-5, this mirror by 4e-5)
+    assert err < 2e-4
+    assert abs(float(A.losses[0]) - float(g["loss_start"])) < 1e-4 and abs(loss_end - float(g["loss_end"])) < 1e-3
