@@ -181,3 +181,58 @@ dist.destroy_process_group()
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
     assert float(line[1]) < 3e-6 and line[2] == "True"
+
+
+def test_alignment_allreduce_nccl_two_gpus(tmp_path):
+    """Alignment / training mode on two GPUs: every rank transforms its shard of the series with its
+    own thetas and pulls it towards ONE shared template; the NCCL all-reduce of the template gradient
+    (the only collective of the path) must give what a single process gets on the whole batch, and
+    the per-series theta gradients must equal the unsharded ones (skipped on a one-GPU box)."""
+    import subprocess, sys, os
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "al.py"
+    script.write_text('''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from libcpab_b200 import Cpab, CpabSequential
+from libcpab_b200.distributed import shard, allreduce_grad_
+rank, ws = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+torch.manual_seed(9)                                   # same global problem on every rank
+Ts = [Cpab([20], backend="pytorch", device="gpu") for _ in range(2)]
+for T in Ts:
+    T.params.points_grad = True
+S = CpabSequential(*Ts)
+n = 64
+thetas = [0.5 * T.sample_transformation(n) for T in Ts]
+data = torch.rand(n, 1, 200, device="cuda")
+template0 = torch.rand(1, 1, 160, device="cuda")
+
+def step(th_list, series):
+    template = template0.clone().requires_grad_(True)
+    ths = [t.clone().requires_grad_(True) for t in th_list]
+    out = S.transform_data(series, ths, outsize=[160])
+    (out - template).square().sum().backward()
+    return template, ths
+
+t_full, th_full = step(thetas, data)                    # the whole batch in one process
+t_loc, th_loc = step([shard(t) for t in thetas], shard(data))
+allreduce_grad_(t_loc)                                  # NCCL all-reduce of the shared parameter's gradient
+e_t = float((t_loc.grad - t_full.grad).abs().max() / t_full.grad.abs().max())
+e_th = max(float((a.grad - shard(b.grad)).abs().max() / b.grad.abs().max()) for a, b in zip(th_loc, th_full))
+worst = torch.tensor([e_t, e_th], device="cuda")
+dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("RESULT", float(worst[0]), float(worst[1]))
+dist.destroy_process_group()
+''' % root)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29535", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    print("alignment on 2 GPUs: template gradient rel diff %s, per-series theta gradients rel diff %s" % (line[1], line[2]))
+    assert float(line[1]) < 3e-6 and float(line[2]) < 1e-6
