@@ -31,6 +31,7 @@ One JSON line is printed by rank 0:
   fast_grad  the same step with CPAB_FLAG_FAST_GRAD (no certificate): what the default mode costs
   cpu_baseline     the reference's own C++ core (oracle/_ref, else the oracle port), host cores
   other_workloads  (N=1) compact records of the other BASELINE configs: cfg1, cfg2, cfg4, cfg5
+  closed_form      (N=1) the opt-in hit-time integrator (2-D, 3-D): fwd+bwd next to the fixed-step kernels, lane utilisation
   alignment_cfg5   (every N) BASELINE configs[4]: 4-warp CpabSequential alignment step, 8192 series
              x 1024 per GPU, with the NCCL all-reduce of the shared template gradient in the step
   cfg4_point_sharded  (N>1) BASELINE configs[3] with the POINTS split over the ranks and dtheta
@@ -717,6 +718,64 @@ def reference_cuda_records(ctx, name, ours):
     }
 
 
+def closed_form_records(ctx, steps):
+    """The opt-in hit-time ("closed-form") integrator of north_star on the 2-D and 3-D BASELINE shapes:
+    transform_grid forward + backward w.r.t. theta, device-timed, next to the fixed-step kernels on the same
+    inputs, with the lane utilisation of its variable-trip-count loop (refill on / off)."""
+    from libcpab_b200 import Cpab, _lib, ops
+    torch = ctx.torch
+    out = {}
+    for name, tess, n_theta, size, kw in (("2d_t10x10vp_b64_512x512", [10, 10], 64, [512, 512], {"volume_perservation": True}),
+                                          ("3d_t4x4x4_b16_128cubed", [4, 4, 4], 16, [128, 128, 128], {})):
+        torch.manual_seed(77)
+        T = Cpab(tess, backend="pytorch", device="gpu", **kw)
+        theta = torch.randn(n_theta, T.params.d, device=ctx.dev, requires_grad=True)
+        grid = T.uniform_meshgrid(size)
+        R = torch.randn(n_theta, len(tess), grid.shape[1], device=ctx.dev)
+        pairs = n_theta * grid.shape[1]
+
+        def step():
+            theta.grad = None
+            (T.transform_grid(grid, theta) * R).sum().backward()
+            return theta.grad
+
+        rec = {}
+        for mode in ("closed_form", "fixed_step"):
+            T.params.closed_form = mode == "closed_form"
+            step(); step()
+            _lib.profile_enable(True)
+            ms = ctx.timed(step, steps) / steps
+            prof = {k: _lib.profile_read(k)[0] / steps for k in _lib.PROFILE_SLOTS}
+            _lib.profile_enable(False)
+            rec[mode] = {"ms_per_step": ms, "value": pairs / (ms * 1e-3), "unit": "pairs/s",
+                         "kernel_ms": {k: round(v, 4) for k, v in prof.items() if v}}
+        T.params.closed_form = True
+        exact = T.transform_grid(grid, theta.detach())
+        T.params.closed_form = False
+        fixed = T.transform_grid(grid, theta.detach())
+        inner = (grid < 1).all(dim=0)
+        rec["max_abs_diff_fixed_step_vs_hit_time"] = float((exact - fixed)[:, :, inner].abs().max())
+        B = torch.as_tensor(np.asarray(T.params.basis), dtype=torch.float32, device=ctx.dev)
+        As = (B @ theta.detach().T).T.reshape(n_theta, -1, len(tess), len(tess) + 1).contiguous()
+        util = {}
+        try:
+            for refill in (0, 1):
+                _lib.set_tuning("closed_refill", refill)
+                _, u, per = ops.closed_form_lane_stats(grid, As, tess)
+                t = ctx.timed(lambda: ops.forward_closed_form(grid, As, tess), 3) / 3
+                util["refill_%d" % refill] = {"lane_utilisation": u, "forward_ms": t}
+                rec["substeps_per_trajectory"] = per
+        finally:
+            _lib.set_tuning("closed_refill", 1)
+        rec["divergence"] = util
+        out[name] = rec
+        del theta, grid, R
+        torch.cuda.empty_cache()
+    out["what"] = ("opt-in exact integrator (not in the reference): transform_grid fwd + bwd wrt theta, theta ~ N(0, I); "
+                   "lane_utilisation = sub-steps executed by lanes / (32 x loop iterations of warps)")
+    return out
+
+
 def run_reference_cuda_arm(args):
     ctx = Ctx()
     if ctx.rank != 0:
@@ -785,6 +844,10 @@ def run_gpu_arm(args):
                                 "kernel_ms_per_step": {k: round(v, 5) for k, v in r["kernel_ms_per_step"].items() if v},
                                 "interp_in_step": r["roofline_interp"]["in_step"], "gpu_launches": r["gpu_launches"]}
             extras["other_workloads"] = others
+            try:
+                extras["closed_form"] = closed_form_records(ctx, max(3, args.steps // 4))
+            except Exception as e:
+                extras["closed_form"] = {"error": repr(e)}
             try:
                 main["_T"] = T
                 extras["vs_reference_cuda"] = reference_cuda_records(ctx, args.workload, main)

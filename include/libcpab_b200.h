@@ -179,11 +179,13 @@ int cpab_b200_rk2_cell_trace(int ndim, const int* nc, int nsteps, int n_theta, l
                              size_t workspace_bytes, int* cells, unsigned char* failed, void* stream);
 
 /*
- * Closed-form ("hit-time") integration, 1-D only; OPT-IN extension, no counterpart in the
- * reference (which integrates with nstepsolver fixed steps in every backend, libcpab/cpab.py:77,
- * libcpab/core/cpab_ops.cpp:240-253).  Implements the algorithm of Freifeld et al., TPAMI 2017:
- * analytic flow to the cell boundary, hit time, cross, repeat to t = 1.  Takes the velocity
- * matrices `As` (not Trels) and no step count.  ndim != 1 returns CPAB_ERR_UNSUPPORTED.
+ * Closed-form ("hit-time") integration; OPT-IN extension, no counterpart in the reference (which
+ * integrates with nstepsolver fixed steps in every backend, libcpab/cpab.py:77,
+ * libcpab/core/cpab_ops.cpp:240-253).  The algorithm BASELINE.json's north_star names (Freifeld et
+ * al., TPAMI 2017): analytic in-cell flow to the cell boundary, hit time, cross, repeat to t = 1.
+ * 1-D: closed-form hit time (cpab_closed1d.cu).  2-D / 3-D: the in-cell flow and the face
+ * functions as Taylor polynomials on sub-steps of ||L|| tau <= 1/2, hit time by bracketing + Newton
+ * (cpab_closednd.cu).  Takes the velocity matrices `As` (not Trels) and no step count.
  */
 int cpab_b200_forward_closed_form(int dtype, int ndim, const int* nc, int n_theta, long nP,
                                   int broadcast, const void* points, const void* As, void* newpoints,
@@ -196,6 +198,18 @@ int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int
                                          const void* basis, const void* grad_out, void* dtheta,
                                          void* dpoints, void* workspace, size_t workspace_bytes,
                                          void* stream);
+
+/*
+ * Diagnostic door (2-D / 3-D): the forward walk of cpab_b200_forward_closed_form, which also counts
+ * how well the variable-trip-count loop fills its warps.  counts (device, 2 x uint64, zeroed here):
+ *   counts[0] = sub-steps executed by lanes, counts[1] = 32 x loop iterations executed by warps;
+ * counts[0] / counts[1] is the lane utilisation.  The tuning key "closed_refill" (1: a lane that
+ * finishes takes the warp's next point, default; 0: the warp waits for its slowest lane) selects
+ * the mitigation that is being measured.
+ */
+int cpab_b200_closed_form_lane_stats(int dtype, int ndim, const int* nc, int n_theta, long nP, int broadcast,
+                                     const void* points, const void* As, void* newpoints,
+                                     unsigned long long* counts, void* stream);
 
 /*
  * Linear / bilinear / trilinear sampling.  Replaces interpolate(ndim, data, grid, outsize),

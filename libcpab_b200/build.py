@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SOURCES = ["cpab_abi.cu", "cpab_integrate.cu", "cpab_adjoint_1d.cu", "cpab_adjoint_2d.cu", "cpab_adjoint_3d.cu",
-           "cpab_expm.cu", "cpab_interp.cu", "cpab_probe.cu", "cpab_closed1d.cu"]
+           "cpab_expm.cu", "cpab_interp.cu", "cpab_probe.cu", "cpab_closed1d.cu", "cpab_closednd.cu"]
 HEADERS = ["cpab_common.cuh", "cpab_cell.cuh", "cpab_f32x2.cuh", "cpab_sample.cuh", "cpab_device.cuh", "cpab_adjoint.cuh",
            os.path.join("..", "..", "include", "libcpab_b200.h")]
 LIB = os.path.join(CSRC, "libcpab_b200.so")

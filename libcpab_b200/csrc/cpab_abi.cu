@@ -254,15 +254,12 @@ int cpab_b200_forward_closed_form(int dtype, int ndim, const int* nc, int n_thet
                                   void* stream)
 {
     if (!check_geom(dtype, ndim, nc)) return kErrArgument;
-    if (ndim != 1) {
-        set_error("closed-form integration exists in 1-D only (the hit time has no closed form in %d-D)", ndim);
-        return kErrUnsupported;
-    }
     REQUIRE(n_theta >= 0 && nP >= 0, "negative size");
     REQUIRE(broadcast == 0 || broadcast == 1, "broadcast must be 0 or 1");
     REQUIRE(n_theta == 0 || nP == 0 || (points && As && newpoints), "NULL pointer argument");
-    return launch_closed1d_forward(dtype, make_geom(ndim, nc), n_theta, nP, broadcast, points, As,
-                                   newpoints, (cudaStream_t)stream);
+    const Geom g = make_geom(ndim, nc);
+    if (ndim == 1) return launch_closed1d_forward(dtype, g, n_theta, nP, broadcast, points, As, newpoints, (cudaStream_t)stream);
+    return launch_closednd_forward(dtype, g, n_theta, nP, broadcast, points, As, newpoints, nullptr, (cudaStream_t)stream);
 }
 
 int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int n_theta, int d,
@@ -272,10 +269,6 @@ int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int
                                          void* stream)
 {
     if (!check_geom(dtype, ndim, nc)) return kErrArgument;
-    if (ndim != 1) {
-        set_error("closed-form integration exists in 1-D only (the hit time has no closed form in %d-D)", ndim);
-        return kErrUnsupported;
-    }
     REQUIRE(n_theta >= 0 && nP >= 0 && d >= 0, "negative size");
     REQUIRE(broadcast == 0 || broadcast == 1, "broadcast must be 0 or 1");
     REQUIRE(n_theta == 0 || d == 0 || (As && basis && dtheta && workspace), "NULL pointer argument");
@@ -286,9 +279,25 @@ int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int
     if (n_theta == 0 || d == 0) return kOk;
     cudaStream_t st = (cudaStream_t)stream;
     CPAB_CUDA_OK(cudaMemsetAsync(workspace, 0, backward_g_bytes(dtype, g, n_theta), st));
-    int rc = launch_closed1d_backward(dtype, g, n_theta, nP, broadcast, points, As, grad_out, workspace, dpoints, st);
+    int rc = ndim == 1 ? launch_closed1d_backward(dtype, g, n_theta, nP, broadcast, points, As, grad_out, workspace, dpoints, st)
+                       : launch_closednd_backward(dtype, g, n_theta, nP, broadcast, points, As, grad_out, workspace, dpoints, st);
     if (rc != kOk) return rc;
-    return launch_grad_epilogue(dtype, workspace, basis, dtheta, n_theta, 2 * g.nc[0], d, st);
+    return launch_grad_epilogue(dtype, workspace, basis, dtheta, n_theta, g.n_cells * ndim * (ndim + 1), d, st);
+}
+
+int cpab_b200_closed_form_lane_stats(int dtype, int ndim, const int* nc, int n_theta, long nP, int broadcast,
+                                     const void* points, const void* As, void* newpoints,
+                                     unsigned long long* counts, void* stream)
+{
+    if (!check_geom(dtype, ndim, nc)) return kErrArgument;
+    REQUIRE(ndim == 2 || ndim == 3, "lane statistics exist for the 2-D / 3-D walk, got ndim = %d", ndim);
+    REQUIRE(n_theta >= 0 && nP >= 0, "negative size");
+    REQUIRE(broadcast == 0 || broadcast == 1, "broadcast must be 0 or 1");
+    REQUIRE(counts != nullptr, "NULL pointer argument");
+    REQUIRE(n_theta == 0 || nP == 0 || (points && As && newpoints), "NULL pointer argument");
+    CPAB_CUDA_OK(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+    return launch_closednd_forward(dtype, make_geom(ndim, nc), n_theta, nP, broadcast, points, As, newpoints,
+                                   counts, (cudaStream_t)stream);
 }
 
 static int check_interp(int dtype, int ndim, int N, int C, const int* in_size, const int* out_size)

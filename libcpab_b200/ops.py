@@ -186,7 +186,7 @@ def rk2_cell_trace(points: torch.Tensor, As: torch.Tensor, nc, nsteps: int, mode
 
 
 def forward_closed_form(points: torch.Tensor, As: torch.Tensor, nc) -> torch.Tensor:
-    """1-D closed-form (hit-time) integration; opt-in extension, not in the reference."""
+    """Closed-form (hit-time) integration in 1-D / 2-D / 3-D; opt-in extension, not in the reference."""
     points, As = _req(points, "points"), _req(As, "As")
     n_theta = As.shape[0]
     broadcast, ndim, nP = _points_layout(points, n_theta)
@@ -196,6 +196,23 @@ def forward_closed_form(points: torch.Tensor, As: torch.Tensor, nc) -> torch.Ten
                                                         broadcast, points.data_ptr(), As.data_ptr(),
                                                         out.data_ptr(), _stream()), "forward_closed_form")
     return out
+
+
+def closed_form_lane_stats(points: torch.Tensor, As: torch.Tensor, nc):
+    """(newpoints, lane utilisation, sub-steps per trajectory) of the 2-D / 3-D hit-time walk: how full
+    the warps of the variable-trip-count loop are (tuning key "closed_refill" selects the mitigation)."""
+    points, As = _req(points, "points"), _req(As, "As")
+    n_theta = As.shape[0]
+    broadcast, ndim, nP = _points_layout(points, n_theta)
+    out = torch.empty((n_theta, ndim, nP), dtype=points.dtype, device=points.device)
+    counts = torch.zeros(2, dtype=torch.int64, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.load().cpab_b200_closed_form_lane_stats(_dtype_code(points), ndim, nc_array(nc), n_theta, nP,
+                                                           broadcast, points.data_ptr(), As.data_ptr(),
+                                                           out.data_ptr(), counts.data_ptr(), _stream()),
+              "closed_form_lane_stats")
+    lanes, slots = (int(v) for v in counts.tolist())
+    return out, lanes / max(slots, 1), lanes / max(n_theta * nP, 1)
 
 
 def backward_theta_closed_form(points, As, basis, grad_out, nc, want_dpoints=False):

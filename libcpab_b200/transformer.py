@@ -125,7 +125,4 @@ def CPAB_transformer(points, theta, params):
         raise RuntimeError("libcpab_b200 runs on CUDA tensors only (backend='pytorch', device='gpu')")
     if points.dtype != theta.dtype:
         raise TypeError("grid and theta must have the same dtype")
-    if getattr(params, "closed_form", False) and params.ndim != 1:
-        raise NotImplementedError("closed_form integration exists in 1-D only: in 2-D/3-D the hit "
-                                  "time of a cell boundary has no closed form")
     return _CpabFunction.apply(points, theta, params)

@@ -533,3 +533,204 @@ def closed_form_1d(points: np.ndarray, As: np.ndarray, nc) -> np.ndarray:
     with np.errstate(divide="ignore", invalid="ignore"):
         phi = np.where(np.abs(z) < 1e-8, 1.0 + z / 2, np.expm1(z) / np.where(z == 0, 1.0, z))
     return (x * np.exp(z) + b * t * phi)[:, None, :]
+
+
+# --------------------------------------------------------------------------------------------
+# closed-form (hit-time) integration in 2-D / 3-D
+# --------------------------------------------------------------------------------------------
+# Faces of the simplices of one square / cube in its local coordinates u in [0,1]^n, inward positive:
+# rows (normal..., offset).  2-D: triangle types of cpab_ops.cpp:94-103; 3-D: tetrahedra of :160-184 in
+# the coordinates of an even cube (cubes of odd i+j+k use (x, y) <- (y, 1-x), :170-174).
+_FACES_2D = {
+    0: [(1, -1, 0), (-1, -1, 1), (0, 1, 0)],
+    1: [(1, -1, 0), (1, 1, -1), (-1, 0, 1)],
+    2: [(-1, 1, 0), (1, 1, -1), (0, -1, 1)],
+    3: [(-1, 1, 0), (-1, -1, 1), (1, 0, 0)],
+}
+_FACES_3D = {
+    0: [(1, 1, -1, 0), (-1, -1, -1, 2), (1, -1, 1, 0), (-1, 1, 1, 0)],
+    1: [(-1, -1, 1, 0), (1, 0, 0, 0), (0, 1, 0, 0), (0, 0, -1, 1)],
+    2: [(1, 1, 1, -2), (-1, 0, 0, 1), (0, -1, 0, 1), (0, 0, -1, 1)],
+    3: [(-1, 1, -1, 0), (1, 0, 0, 0), (0, -1, 0, 1), (0, 0, 1, 0)],
+    4: [(1, -1, -1, 0), (-1, 0, 0, 1), (0, 1, 0, 0), (0, 0, 1, 0)],
+}
+
+
+def _simplex_faces(ndim: int, typ: int, parity: int):
+    rows = np.array((_FACES_2D if ndim == 2 else _FACES_3D)[typ], dtype=np.float64)
+    N, D = rows[:, :ndim].copy(), rows[:, ndim].copy()
+    if ndim == 3 and parity:      # a x' + b y' + c z + d with x' = y, y' = 1 - x  =  -b x + a y + c z + (d + b)
+        N, D = np.stack([-rows[:, 1], rows[:, 0], rows[:, 2]], axis=1), rows[:, 3] + rows[:, 1]
+    return N, D
+
+
+def _simplex_type(ndim: int, u: np.ndarray, parity: int) -> int:
+    """Simplex of a local point (also outside [0,1]^n: the partition continued by its planes)."""
+    if ndim == 2:
+        x, y = u
+        if x < y:
+            return 2 if 1 - x < y else 3
+        return 1 if 1 - x < y else 0
+    x, y, z = u
+    if parity:
+        x, y = y, 1 - x
+    if -x - y + z >= 0:
+        return 1
+    if x + y + z - 2 >= 0:
+        return 2
+    if -x + y - z >= 0:
+        return 3
+    if x - y - z >= 0:
+        return 4
+    return 0
+
+
+_GEOMETRY_CHECKED = set()
+
+
+def _check_geometry(nc) -> None:
+    """The face tables against the pinned cell search: on random points of every cube, membership
+    by the tables' inequalities is membership by findcellidx (cpab_ops.cpp:33-184)."""
+    key = tuple(nc)
+    if key in _GEOMETRY_CHECKED:
+        return
+    ndim = len(nc)
+    spc = {2: 4, 3: 5}[ndim]
+    rng = np.random.default_rng(11)
+    u = rng.uniform(0.01, 0.99, size=(ndim, 4000))
+    for cube in range(int(np.prod(nc))):
+        idx, s = [], cube
+        for j in range(ndim):
+            idx.append(s % nc[j]); s //= nc[j]
+        parity = (sum(idx) & 1) if ndim == 3 else 0
+        pts = (np.array(idx)[:, None] + u) / np.array(nc, dtype=np.float64)[:, None]
+        cells = findcellidx(pts, nc)
+        for typ in range(spc):
+            N, D = _simplex_faces(ndim, typ, parity)
+            F = N @ u + D[:, None]
+            mine = (F > 1e-9).all(axis=0)
+            edge = (np.abs(F) <= 1e-9).any(axis=0)
+            theirs = cells == spc * cube + typ
+            if ndim == 3:       # sic: the reference clamps z to nz * inc_x (cpab_ops.cpp:141), which cuts the top off
+                edge |= pts[2] >= nc[2] / nc[0] - 1e-6      # a tessellation with nz < nx; the tables hold the intended geometry
+            if not np.array_equal(mine[~edge], theirs[~edge]):
+                raise RuntimeError("simplex face table disagrees with findcellidx (cube %d type %d)" % (cube, typ))
+    _GEOMETRY_CHECKED.add(key)
+
+
+def closed_form_nd(points: np.ndarray, As: np.ndarray, nc, stats: dict | None = None) -> np.ndarray:
+    """Exact unit-time flow of a 2-D / 3-D CPA field by the hit-time algorithm of north_star:
+    inside a simplex x~(t) = expm(t [[L, b], [0, 0]]) x~; find the time at which the trajectory
+    reaches a face, cross into the neighbouring simplex, repeat until t = 1.
+
+    PARITY UNPINNED (as closed_form_1d): the reference has no such integrator.  This float64 checker
+    uses scipy's expm and a bracketing root finder (nothing in common with the kernels' Taylor
+    polynomials); its simplex geometry is verified against the pinned cell search (_check_geometry)
+    and it is anchored by tests/test_closed_form_oracle.py: the float64 RK2 flow of the same field
+    (rk2_flow, cpab_ops.cpp:289-366 in double) converges to it at second order.
+    Outside the unit box (only trajectories of tessellations without zero boundary get there) the
+    field is continued by the planes of the boundary cubes: an outer face is never crossed, the
+    other faces are extended -- NOT the reference's rules for outside points (cpab_ops.cpp:47-92,
+    119-136), which are discontinuous; `stats["outside"]` marks those trajectories.
+
+    points [n,nP] or [n_theta,n,nP]; As [n_theta,nC,n,n+1] -> [n_theta,n,nP] float64.
+    """
+    from scipy.linalg import expm
+    from scipy.optimize import brentq
+    As = np.asarray(As, dtype=np.float64)
+    nc = [int(v) for v in nc]
+    ndim = len(nc)
+    spc = {2: 4, 3: 5}[ndim]
+    _check_geometry(nc)
+    n_theta = As.shape[0]
+    pts = np.asarray(points, dtype=np.float64)
+    pts = np.broadcast_to(pts if pts.ndim == 3 else pts[None], (n_theta, ndim, pts.shape[-1]))
+    out = np.empty((n_theta, ndim, pts.shape[-1]))
+    outside = np.zeros((n_theta, pts.shape[-1]), dtype=bool)
+    ncv = np.array(nc, dtype=np.float64)
+    eps_on, nodes = 1e-12, 16
+    segs = 0
+    for th in range(n_theta):
+        for i in range(pts.shape[-1]):
+            x = pts[th, :, i].copy()
+            t_rem = 1.0
+            # start simplex: inside the box findcellidx up to ties on faces (_check_geometry), outside it the
+            # continuation of the boundary cubes' planes that the walk itself uses
+            idx = np.clip(np.floor(x * ncv), 0, ncv - 1).astype(np.int64)
+            typ = _simplex_type(ndim, x * ncv - idx, int(idx.sum() & 1) if ndim == 3 else 0)
+            closed = set()
+            for _ in range(10000):
+                parity = int(idx.sum() & 1) if ndim == 3 else 0
+                N, D = _simplex_faces(ndim, typ, parity)
+                c = spc * int(idx[0] + (idx[1] * nc[0] if ndim > 1 else 0) + (idx[2] * nc[0] * nc[1] if ndim > 2 else 0)) + typ
+                At = np.zeros((ndim + 1, ndim + 1))
+                At[:ndim] = As[th, c]
+                norm = np.abs(At[:ndim, :ndim]).sum(axis=1).max()
+                tau = min(t_rem, 0.5 / norm) if norm > 0 else t_rem
+                xt = np.append(x, 1.0)
+
+                def local(t):     # the trajectory of this simplex's own flow, local coordinates
+                    return (expm(t * At) @ xt)[:ndim] * ncv - idx
+
+                def face(t, p):   # inward-positive face function p and its time derivative
+                    e = expm(t * At) @ xt
+                    return N[p] @ (e[:ndim] * ncv - idx) + D[p], N[p] @ ((At @ e)[:ndim] * ncv)
+
+                hit_t, hit_p, probe = None, None, None
+                for p in range(N.shape[0]):
+                    if p in closed:
+                        continue
+                    axis = np.flatnonzero(N[p])
+                    if len(axis) == 1:      # a box face: outer if the cube is at that edge of the domain
+                        j = int(axis[0])
+                        if (N[p, j] > 0 and idx[j] == 0) or (N[p, j] < 0 and idx[j] == nc[j] - 1):
+                            continue
+                    lim = tau if hit_t is None else hit_t
+                    ts = np.linspace(0.0, lim, nodes + 1)
+                    fd = [face(t, p) for t in ts]
+                    # exit = the first time f(t) + eps turns negative (a point on the face is still inside)
+                    if fd[0][0] < -eps_on:          # already outside: leave at once
+                        if hit_t is None or 0.0 < hit_t:
+                            hit_t, hit_p, probe = 0.0, p, 0.0
+                        continue
+                    for m in range(1, nodes + 1):
+                        t_m, (f_m, d_m) = ts[m], fd[m]
+                        if f_m >= -eps_on and fd[m - 1][1] < 0 and d_m > 0:      # a minimum in between
+                            t_min = brentq(lambda t: face(t, p)[1], ts[m - 1], ts[m], xtol=1e-15, rtol=1e-15)
+                            if face(t_min, p)[0] < -eps_on:
+                                t_m, (f_m, d_m) = t_min, face(t_min, p)
+                        if f_m < -eps_on:
+                            t_p = brentq(lambda t: face(t, p)[0] + eps_on, ts[m - 1], t_m, xtol=1e-15, rtol=1e-15)
+                            after = min(t_m, t_p + 4 * eps_on / max(abs(face(t_p, p)[1]), 1e-300))
+                            if hit_t is None or t_p < hit_t:
+                                hit_t, hit_p, probe = t_p, p, after
+                            break
+                step = tau if hit_t is None else hit_t
+                x_new = (expm(step * At) @ xt)[:ndim]
+                t_rem -= step
+                segs += 1
+                if step > 0:
+                    closed = set()
+                if (x_new < -1e-9).any() or (x_new > 1 + 1e-9).any():
+                    outside[th, i] = True
+                if hit_t is not None:
+                    u = local(probe)
+                    idx2 = idx.copy()
+                    for j in range(ndim):
+                        if u[j] < 0 and idx2[j] > 0:
+                            idx2[j] -= 1; u[j] += 1
+                        elif u[j] > 1 and idx2[j] < nc[j] - 1:
+                            idx2[j] += 1; u[j] -= 1
+                    typ2 = _simplex_type(ndim, u, int(idx2.sum() & 1) if ndim == 3 else 0)
+                    if typ2 != typ or (idx2 != idx).any():
+                        idx, typ, closed = idx2, typ2, set()
+                    else:
+                        closed.add(hit_p)
+                x = x_new
+                if t_rem <= 0:
+                    break
+            out[th, :, i] = x
+    if stats is not None:
+        stats["segments"] = segs
+        stats["outside"] = outside
+    return out

@@ -120,11 +120,168 @@ def test_api_switch_and_flow_properties_at_full_size():
     assert bool((T.transform_grid(grid, T.identity(3)) == grid[None]).all())
 
 
-def test_closed_form_is_one_dimensional_only():
-    from libcpab_b200 import Cpab, _lib, ops
-    T = Cpab([3, 3], backend="pytorch", device="gpu")
+# ---- 2-D / 3-D: the hit-time walk on Taylor polynomials (cpab_closednd.cu) ----------------------------
+ND = [("d2_t3x3", 150), ("d2_t10x10_vp", 150), ("d3_t2x2x2", 120), ("d3_t3x2x2_vp", 60), ("d2_t2x3_free_vp", 80),
+      ("d3_t2x2x2_free", 80)]
+
+
+def _nd_case(name, npts, n_theta=3):
+    g = load_golden(name)
+    nc = g["nc"].tolist()
+    theta = g["theta"][-n_theta:].astype(np.float64)
+    As = O.theta_to_affine(g["B"], theta, nc, np.float64)
+    grid = g["grid"].astype(np.float64)
+    grid = grid[:, ::max(1, grid.shape[1] // npts)]
+    return g, nc, theta, As, grid
+
+
+@pytest.mark.parametrize("name,npts", ND)
+def test_nd_forward_matches_checker(name, npts):
+    """Kernel (Taylor polynomials, Newton on the face polynomials) against the checker (scipy expm,
+    brentq): float64 to 1e-10, float32 to 1e-5 relative -- every trajectory, including the ones of the
+    free-boundary tessellations that leave the unit box (both continue the boundary cubes' planes)."""
+    from libcpab_b200 import ops
+    g, nc, theta, As, grid = _nd_case(name, npts)
+    st = {}
+    ref = O.closed_form_nd(grid, As, nc, st)
+    got64 = ops.forward_closed_form(dev(grid), dev(As), nc).cpu().numpy()
+    e64 = np.abs(got64 - ref).max()
+    got32 = ops.forward_closed_form(dev(grid, torch.float32), dev(As, torch.float32), nc).cpu().numpy()
+    e32 = np.abs(got32 - ref).max()
+    print("%s: float64 max |err| %.2e, float32 %.2e (bound %.1e), %d of %d trajectories leave the box, %.1f sub-steps each"
+          % (name, e64, e32, 1e-6 * flow_gain(As), st["outside"].sum(), st["outside"].size, st["segments"] / st["outside"].size))
+    assert e64 < 1e-10
+    assert e32 < 1e-6 * flow_gain(As) + 2e-6
+
+
+@pytest.mark.parametrize("name,npts", [("d2_t3x3", 64), ("d3_t2x2x2", 64), ("d2_t10x10_vp", 64)])
+def test_nd_gradient_matches_differenced_checker(name, npts):
+    """d/dtheta and d/dpoints: float64 kernel against central differences of the CHECKER along random
+    directions, and against central differences of the kernel's own float64 forward for every theta
+    component; float32 kernel against the float64 one."""
+    from libcpab_b200 import ops
+    g, nc, theta, As, grid = _nd_case(name, npts, n_theta=2)
+    B = g["B"]
+    rng = np.random.default_rng(3)
+    gout = rng.normal(size=(theta.shape[0], len(nc), grid.shape[1]))
+    dth, dpts = ops.backward_theta_closed_form(dev(grid), dev(As), dev(B), dev(gout), nc, want_dpoints=True)
+    dth, dpts = dth.cpu().numpy(), dpts.cpu().numpy()
+
+    def loss_checker(th):
+        return float((O.closed_form_nd(grid, O.theta_to_affine(B, th, nc, np.float64), nc) * gout).sum())
+
+    def loss_kernel(th):
+        A = O.theta_to_affine(B, th, nc, np.float64)
+        return float((ops.forward_closed_form(dev(grid), dev(A), nc).cpu().numpy() * gout).sum())
+
+    eps = 1e-6
+    for k in range(2):                                  # checker, random directions
+        dirn = rng.normal(size=theta.shape)
+        fd = (loss_checker(theta + eps * dirn) - loss_checker(theta - eps * dirn)) / (2 * eps)
+        an = float((dth * dirn).sum())
+        print("%s: directional derivative %.9e, differenced checker %.9e" % (name, an, fd))
+        assert abs(an - fd) < 2e-6 * max(1.0, abs(fd))
+    fd = np.zeros_like(theta)                           # kernel forward, every component
+    for t in range(theta.shape[0]):
+        for k in range(theta.shape[1]):
+            e = np.zeros_like(theta); e[t, k] = eps
+            fd[t, k] = (loss_kernel(theta + e) - loss_kernel(theta - e)) / (2 * eps)
+    print("%s: dtheta vs differenced forward: rel err %.2e" % (name, rel_err(dth, fd)))
+    assert rel_err(dth, fd) < 2e-6
+    # d/dpoints: shift all points (central differences of the kernel's forward, one coordinate at a time)
+    fdp = np.zeros_like(dpts)
+    h = 1e-7
+    for j in range(len(nc)):
+        sh = np.zeros((len(nc), 1)); sh[j] = h
+        up = ops.forward_closed_form(dev(grid + sh), dev(As), nc).cpu().numpy()
+        dn = ops.forward_closed_form(dev(grid - sh), dev(As), nc).cpu().numpy()
+        fdp[:, j] = ((up - dn) / (2 * h) * gout).sum(axis=1)
+    interior = ((grid > 1e-3) & (grid < 1 - 1e-3)).all(axis=0)
+    print("%s: dpoints vs differenced forward: rel err %.2e" % (name, rel_err(dpts[:, :, interior], fdp[:, :, interior])))
+    assert rel_err(dpts[:, :, interior], fdp[:, :, interior]) < 1e-5
+    dth32, _ = ops.backward_theta_closed_form(dev(grid, torch.float32), dev(As, torch.float32), dev(B, torch.float32),
+                                              dev(gout, torch.float32), nc)
+    print("%s: float32 dtheta vs float64: rel err %.2e" % (name, rel_err(dth32.cpu().numpy(), dth)))
+    assert rel_err(dth32.cpu().numpy(), dth) < 1e-4
+
+
+@pytest.mark.parametrize("nc", [[3, 3], [2, 2, 2]])
+def test_nd_gradient_at_the_identity(nc):
+    """theta = 0: the field vanishes, and the exact gradient G_c = int lambda [x;1]^T dt over the cell of
+    each (resting) point equals the fixed-step adjoint's, which is exact for a zero field."""
+    from libcpab_b200 import ops
+    name = "d2_t3x3" if len(nc) == 2 else "d3_t2x2x2"
+    g = load_golden(name)
+    B = g["B"]
+    grid = g["grid"].astype(np.float64)[:, ::5]
+    As = np.zeros((2, O.n_cells(nc), len(nc), len(nc) + 1))
+    rng = np.random.default_rng(4)
+    gout = rng.normal(size=(2, len(nc), grid.shape[1]))
+    dth, dpts = ops.backward_theta_closed_form(dev(grid), dev(As), dev(B), dev(gout), nc, want_dpoints=True)
+    ref, _ = ops.backward_theta(dev(grid), dev(As), dev(B), dev(gout), nc, 50)
+    assert float(ref.abs().max()) > 1e-3
+    assert rel_err(dth.cpu().numpy(), ref.cpu().numpy()) < 1e-9
+    assert np.allclose(dpts.cpu().numpy(), gout)
+
+
+@pytest.mark.parametrize("nc,size,n_theta", [([10, 10], [256, 256], 16), ([4, 4, 4], [48, 48, 48], 4)])
+def test_nd_api_switch_and_flow_properties(nc, size, n_theta):
+    from libcpab_b200 import Cpab
+    torch.manual_seed(0)
+    T = Cpab(nc, backend="pytorch", device="gpu", volume_perservation=len(nc) == 2)
     T.params.closed_form = True
-    with pytest.raises(NotImplementedError):
-        T.transform_grid(T.uniform_meshgrid([8, 8]), T.sample_transformation(2))
-    with pytest.raises(_lib.CpabError, match="1-D only"):
-        ops.forward_closed_form(torch.zeros(2, 8, device="cuda"), torch.zeros(1, 36, 2, 3, device="cuda"), [3, 3])
+    theta = (0.5 * T.sample_transformation(n_theta)).requires_grad_(True)
+    grid = T.uniform_meshgrid(size)
+    out = T.transform_grid(grid, theta)
+    assert tuple(out.shape) == (n_theta, len(nc), grid.shape[1]) and bool(torch.isfinite(out).all())
+    assert float(out.min()) > -1e-6 and float(out.max()) < 1 + 1e-6          # zero boundary: the box maps to itself
+    back = T.transform_grid(out.detach(), -theta.detach())                     # inverse flow
+    print("inverse flow error %.2e" % float((back - grid[None]).abs().max()))
+    assert float((back - grid[None]).abs().max()) < 2e-5
+    out.square().sum().backward()
+    assert bool(torch.isfinite(theta.grad).all()) and float(theta.grad.abs().max()) > 0
+    T.params.closed_form = False
+    fixed = T.transform_grid(grid, theta.detach())
+    # (away from the upper faces: a coordinate of exactly 1 sends the reference's float32 cell search to the
+    # wrong simplex of the last cube, cpab_ops.cpp:139-148 / SURVEY.md 7.3 -- the fixed-step kernels reproduce that)
+    inner = (grid < 1).all(dim=0)
+    diff = (fixed - out.detach())[:, :, inner].abs().max()
+    print("fixed-step (50) vs hit-time: %.2e (all points: %.2e)" % (float(diff), float((fixed - out.detach()).abs().max())))
+    assert float(diff) < 5e-3
+    T.params.closed_form = True
+    assert float((T.transform_grid(grid, T.identity(2)) - grid[None]).abs().max()) < 1e-6
+    # transform_data goes through the same switch
+    data = torch.rand(n_theta, 1, *size, device="cuda")
+    img = T.transform_data(data, theta.detach(), size)
+    assert tuple(img.shape) == tuple(data.shape) and bool(torch.isfinite(img).all())
+
+
+@pytest.mark.parametrize("nc,size,n_theta", [([10, 10], [256, 256], 32), ([4, 4, 4], [64, 64, 64], 4)])
+def test_nd_lane_utilisation_with_and_without_refill(nc, size, n_theta):
+    """Divergence of the crossing loop, measured: share of the warps' loop slots that do work."""
+    from libcpab_b200 import Cpab, _lib, ops
+    torch.manual_seed(1)
+    T = Cpab(nc, backend="pytorch", device="gpu")
+    theta = T.sample_transformation(n_theta)
+    grid = T.uniform_meshgrid(size)
+    B = torch.as_tensor(np.asarray(T.params.basis), dtype=torch.float32, device="cuda")
+    As = (B @ theta.T).T.reshape(n_theta, -1, len(nc), len(nc) + 1).contiguous()
+    res = {}
+    try:
+        for refill in (0, 1):
+            _lib.set_tuning("closed_refill", refill)
+            out, util, per_traj = ops.closed_form_lane_stats(grid, As, nc)
+            res[refill] = (out, util, per_traj)
+    finally:
+        _lib.set_tuning("closed_refill", 1)
+    print("nc %s: lane utilisation %.3f without refill, %.3f with; %.2f sub-steps per trajectory"
+          % (nc, res[0][1], res[1][1], res[1][2]))
+    assert torch.equal(res[0][0], res[1][0])                 # the same trajectories either way
+    assert res[1][1] > res[0][1] and res[1][1] > 0.85
+    assert abs(res[0][2] - res[1][2]) < 1e-9
+
+
+def test_closed_form_rejects_bad_arguments():
+    from libcpab_b200 import _lib, ops
+    with pytest.raises(_lib.CpabError):
+        ops.closed_form_lane_stats(torch.zeros(1, 8, device="cuda"), torch.zeros(1, 4, 1, 2, device="cuda"), [4])
