@@ -39,7 +39,7 @@ class Cpab(object):
         p.use_slow = False
         p.fast_math = False        # extension: FMA-contracted forward (not bit-exact with the CPU ref)
         p.points_grad = False      # extension: return dL/dpoints (reference returns None)
-        p.closed_form = False      # extension (1-D): exact hit-time integration instead of nstepsolver steps
+        p.closed_form = False      # extension: exact hit-time integration instead of nstepsolver steps
         # transform_data as one forward + one backward kernel (identical results, 5 launches instead
         # of 8): None = automatic (1-D, where the fused accesses stay unit-stride, and launch-bound
         # sizes; measured break-even ~8M pairs in 2-D/3-D, profiles/r01_fused_vs_unfused.txt),

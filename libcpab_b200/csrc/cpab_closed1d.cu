@@ -6,10 +6,10 @@
 // the next cell, repeat until t = 1 -- following Freifeld, Hauberg, Batmanghelich, Fisher,
 // "Transformations based on continuous piecewise-affine velocity fields" (TPAMI 2017), where
 // the construction is closed-form in one dimension.  It is an OPT-IN mode
-// (Cpab.params.closed_form = True, 1-D only): parity with the reference is defined against the
+// (Cpab.params.closed_form = True; this file is the 1-D case): parity with the reference is defined against the
 // fixed-step kernels; this mode converges to the reference's semantics as nstepsolver -> inf and
 // is validated that way (tests/test_gpu_closed_form.py).  In 2-D/3-D the hit time is the root of
-// a sum of exponentials and has no closed form; the mode raises there.
+// a sum of exponentials and has no closed form; cpab_closednd.cu works with its series there.
 //
 // Within cell c, v(x) = a x + b:
 //     psi(x0, t) = x0 e^{at} + b t phi1(at),             phi1(z) = (e^z - 1)/z

@@ -48,8 +48,11 @@ def walk(x, As, nc, verbose=False):
                 if (n[ax] > 0 and idx[ax] == 0) or (n[ax] < 0 and idx[ax] == nc[ax] - 1): continue
             a = ck @ n; a[0] += d
             a[0] += eps
-            tprev, fprev, dprev = 0.0, a[0], a[1]
             lim = best
+            r = abs(a[K])
+            for k in range(K - 1, 1, -1): r = r * lim + abs(a[k])
+            if a[0] + min(0.0, a[1] * lim) - r * lim * lim > 0: continue
+            tprev, fprev, dprev = 0.0, a[0], a[1]
             found = a[0] < 0
             cand, after = 0.0, 0.0
             m = 1

@@ -30,7 +30,7 @@ gout = torch.randn(n_theta, len(tess), grid.shape[1], device="cuda")
 g2 = torch.randn_like(data)
 for _ in range(reps):
     As, Tr = ops.theta_to_trels(theta, Bt, tess, 50)
-    if which == "1d":
+    if which == "1d" or "closed" in sys.argv:
         ops.forward_closed_form(grid, As, tess)
         ops.backward_theta_closed_form(grid, As, B, gout, tess)
     gt = ops.forward(grid, Tr, tess, 50)
