@@ -38,7 +38,7 @@
 // The backward kernel first walks forward to x(1), then walks the REVERSED field (-A) back from
 // x(1) -- the same hit-time code, the same cells in reverse order up to rounding, no trajectory
 // storage -- carrying lambda'(r) = expm(r L'^T) lambda' as a second Taylor polynomial and adding
-// int lambda u^T dr per sub-step by Gauss-Legendre quadrature (5 / 8 nodes).  G goes through the same
+// int lambda u^T dr per sub-step by Gauss-Legendre quadrature (3 / 8 nodes).  G goes through the same
 // G.B epilogue as the fixed-step adjoint; lambda at t = 0 is dL/dpoints.
 #include "cpab_device.cuh"
 
@@ -65,12 +65,13 @@ __constant__ float c_faces3[5][4][4] = {
 
 template <typename T> struct Cf;
 template <> struct Cf<float> {
-    static constexpr int K = 8, Q = 5, kNewton = 4, kScanNodes = 4;     // (2 nodes: 1e-4 errors on 16 x 256^2 trajectories, measured)
+    static constexpr int K = 8, Q = 3, kNewton = 4, kScanNodes = 4;     // (2 nodes: 1e-4 errors on 16 x 256^2 trajectories, measured)
     static constexpr float kEps = 1e-6f;        // x max(nc): |g| below this is "on the face"
+    // 3-point Gauss-Legendre on [0, 1]: error 5e-7 (2 rho)^6 of a sub-step's contribution, below float's own rounding
     static __device__ __forceinline__ void gl(int q, float& x, float& w)
     {
-        const float xs[5] = {0.046910077030668f, 0.230765344947158f, 0.5f, 0.769234655052842f, 0.953089922969332f};
-        const float ws[5] = {0.118463442528095f, 0.239314335249683f, 0.284444444444444f, 0.239314335249683f, 0.118463442528095f};
+        const float xs[3] = {0.112701665379258f, 0.5f, 0.887298334620742f};
+        const float ws[3] = {0.277777777777778f, 0.444444444444444f, 0.277777777777778f};
         x = xs[q]; w = ws[q];
     }
 };
@@ -100,6 +101,10 @@ template <typename T, int NDIM> struct Walker {
     T lam[NDIM];                    // dL/dx, global
     T iu[NDIM][NDIM], i1[NDIM];     // int lambda' u^T dr, int lambda' dr over the stay in the current simplex
 };
+
+// cell width 1 / n (the division costs a dozen instructions a time)
+__device__ __forceinline__ float width_of(const Geom& g, int j, float) { return g.w[j]; }
+__device__ __forceinline__ double width_of(const Geom& g, int j, double) { return g.wd[j]; }
 
 template <int NDIM> __device__ __forceinline__ int parity_of(const int* idx)
 {
@@ -180,7 +185,7 @@ __device__ __forceinline__ void flush_cell(const Geom& g, Walker<T, NDIM>& w, T*
         const T nr = (T)g.nc[r];
 #pragma unroll
         for (int cc = 0; cc < NDIM; ++cc)
-            v[r * M + cc] = nr * (w.iu[r][cc] + (T)w.idx[cc] * w.i1[r]) / (T)g.nc[cc];
+            v[r * M + cc] = nr * (w.iu[r][cc] + (T)w.idx[cc] * w.i1[r]) * width_of(g, cc, (T)0);
         v[r * M + NDIM] = nr * w.i1[r];
     }
     red_cell<NDIM * M>(Gt + (size_t)c * (NDIM * M), v);
@@ -213,7 +218,7 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
         T acc = A[r * M + NDIM], row = (T)0;
 #pragma unroll
         for (int cc = 0; cc < NDIM; ++cc) {
-            const T wc = (T)1 / (T)g.nc[cc];
+            const T wc = width_of(g, cc, (T)0);
             acc = Num<T>::fma(A[r * M + cc], (T)w.idx[cc] * wc, acc);
             Lp[r][cc] = nr * A[r * M + cc] * wc;
             row += fabs(Lp[r][cc]);
@@ -345,7 +350,7 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
         // lambda'(r) = expm(r L'^T) lambda' along the reversed walk: l_{j+1} = -(sgn L')^T l_j / (j+1)
         T lk[K + 1][NDIM];
 #pragma unroll
-        for (int j = 0; j < NDIM; ++j) lk[0][j] = w.lam[j] / (T)g.nc[j];
+        for (int j = 0; j < NDIM; ++j) lk[0][j] = w.lam[j] * width_of(g, j, (T)0);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const T inv = -(T)1 / (T)(k + 1);
@@ -388,7 +393,7 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
         }
     }
 #pragma unroll
-    for (int j = 0; j < NDIM; ++j) w.x[j] = ((T)w.idx[j] + un[j]) / (T)g.nc[j];
+    for (int j = 0; j < NDIM; ++j) w.x[j] = ((T)w.idx[j] + un[j]) * width_of(g, j, (T)0);
     w.trem -= best;
     w.steps += 1;
     const bool done = !(w.trem > (T)0);
