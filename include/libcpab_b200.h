@@ -199,6 +199,15 @@ int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int
                                          void* dpoints, void* workspace, size_t workspace_bytes,
                                          void* stream);
 
+/* The same with the forward's output at hand (`newpoints` [n_theta, ndim, nP], may be NULL): in 2-D / 3-D the
+ * adjoint walks the reversed field back from x(1), and takes x(1) from here instead of walking forward to it
+ * first (a quarter of the kernel's time).  1-D ignores it. */
+int cpab_b200_backward_theta_closed_form_from(int dtype, int ndim, const int* nc, int n_theta, int d,
+                                              long nP, int broadcast, const void* points, const void* As,
+                                              const void* basis, const void* grad_out, const void* newpoints,
+                                              void* dtheta, void* dpoints, void* workspace,
+                                              size_t workspace_bytes, void* stream);
+
 /*
  * Diagnostic door (2-D / 3-D): the forward walk of cpab_b200_forward_closed_form, which also counts
  * how well the variable-trip-count loop fills its warps.  counts (device, 2 x uint64, zeroed here):

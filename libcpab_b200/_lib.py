@@ -47,6 +47,8 @@ SIGNATURES = {
     "cpab_b200_forward_closed_form": (_i, [_i, _i, _ip, _i, _l, _i, _vp, _vp, _vp, _vp]),
     "cpab_b200_backward_theta_closed_form": (_i, [_i, _i, _ip, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp,
                                                   _vp, _vp, _sz, _vp]),
+    "cpab_b200_backward_theta_closed_form_from": (_i, [_i, _i, _ip, _i, _i, _l, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                       _vp, _vp, _sz, _vp]),
     "cpab_b200_closed_form_lane_stats": (_i, [_i, _i, _ip, _i, _l, _i, _vp, _vp, _vp, _vp, _vp]),
     "cpab_b200_interpolate_forward": (_i, [_i, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp]),
     "cpab_b200_transform_data_forward": (_i, [_i, _i, _i, _ip, _i, _i, _i, _ip, _ip, _vp, _vp, _vp, _vp, _vp, _vp]),

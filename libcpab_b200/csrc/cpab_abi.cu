@@ -268,6 +268,16 @@ int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int
                                          void* dpoints, void* workspace, size_t workspace_bytes,
                                          void* stream)
 {
+    return cpab_b200_backward_theta_closed_form_from(dtype, ndim, nc, n_theta, d, nP, broadcast, points, As, basis,
+                                                     grad_out, nullptr, dtheta, dpoints, workspace, workspace_bytes, stream);
+}
+
+int cpab_b200_backward_theta_closed_form_from(int dtype, int ndim, const int* nc, int n_theta, int d,
+                                              long nP, int broadcast, const void* points, const void* As,
+                                              const void* basis, const void* grad_out, const void* newpoints,
+                                              void* dtheta, void* dpoints, void* workspace,
+                                              size_t workspace_bytes, void* stream)
+{
     if (!check_geom(dtype, ndim, nc)) return kErrArgument;
     REQUIRE(n_theta >= 0 && nP >= 0 && d >= 0, "negative size");
     REQUIRE(broadcast == 0 || broadcast == 1, "broadcast must be 0 or 1");
@@ -280,7 +290,7 @@ int cpab_b200_backward_theta_closed_form(int dtype, int ndim, const int* nc, int
     cudaStream_t st = (cudaStream_t)stream;
     CPAB_CUDA_OK(cudaMemsetAsync(workspace, 0, backward_g_bytes(dtype, g, n_theta), st));
     int rc = ndim == 1 ? launch_closed1d_backward(dtype, g, n_theta, nP, broadcast, points, As, grad_out, workspace, dpoints, st)
-                       : launch_closednd_backward(dtype, g, n_theta, nP, broadcast, points, As, grad_out, workspace, dpoints, st);
+                       : launch_closednd_backward(dtype, g, n_theta, nP, broadcast, points, As, grad_out, newpoints, workspace, dpoints, st);
     if (rc != kOk) return rc;
     return launch_grad_epilogue(dtype, workspace, basis, dtheta, n_theta, g.n_cells * ndim * (ndim + 1), d, st);
 }

@@ -35,7 +35,7 @@
 // crossing (the jump would be (v- - v+) dt*/dtheta = 0): the exact gradient is the in-cell
 // variational equation integrated piecewise, in adjoint form
 //     dL/dtheta = sum_c <B_c, G_c>,   G_c = int_{t: x(t) in c} lambda(t) [x(t); 1]^T dt,   lambda' = -L_c^T lambda.
-// The backward kernel first walks forward to x(1), then walks the REVERSED field (-A) back from
+// The backward kernel first walks forward to x(1) (or takes x(1) from the caller), then walks the REVERSED field (-A) back from
 // x(1) -- the same hit-time code, the same cells in reverse order up to rounding, no trajectory
 // storage -- carrying lambda'(r) = expm(r L'^T) lambda' as a second Taylor polynomial and adding
 // int lambda u^T dr per sub-step by Gauss-Legendre quadrature (3 / 8 nodes).  G goes through the same
@@ -491,6 +491,18 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     Walker<T, NDIM> w;
     bool active = false, reverse = false;
     long i = 0;
+    auto begin_reverse = [&]() {
+        w.trem = (T)1;
+        w.steps = 0;
+        w.closed = 0u;
+#pragma unroll
+        for (int r = 0; r < NDIM; ++r) {
+            w.lam[r] = BACKWARD ? gout[(size_t)theta * NDIM * nP + i + (long)r * nP] : (T)0;
+            w.i1[r] = (T)0;
+#pragma unroll
+            for (int cc = 0; cc < NDIM; ++cc) w.iu[r][cc] = (T)0;
+        }
+    };
     unsigned long long lane_steps = 0, warp_iters = 0;
     for (;;) {
         if (refill || !__any_sync(full, active)) {
@@ -498,10 +510,14 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
             const long ni = next + __popc(m & ((1u << lane) - 1u));
             if (!active && ni < wend) {
                 i = ni;
+                // backward with the forward's output at hand (`out`, an input then): start the reverse walk there
+                const bool from_x1 = BACKWARD && out != nullptr;
 #pragma unroll
-                for (int j = 0; j < NDIM; ++j) w.x[j] = src[i + (long)j * nP];
+                for (int j = 0; j < NDIM; ++j)
+                    w.x[j] = from_x1 ? out[(size_t)theta * NDIM * nP + i + (long)j * nP] : src[i + (long)j * nP];
                 start_walk<T, NDIM>(g, w);
-                reverse = false;
+                reverse = from_x1;
+                if (from_x1) begin_reverse();
                 active = true;
             }
             next += __popc(m);
@@ -516,16 +532,7 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
             if (fin) {
                 if (BACKWARD && !reverse) {      // x(1) reached: walk the reversed field back with the adjoint
                     reverse = true;
-                    w.trem = (T)1;
-                    w.steps = 0;
-                    w.closed = 0u;
-#pragma unroll
-                    for (int r = 0; r < NDIM; ++r) {
-                        w.lam[r] = gout[(size_t)theta * NDIM * nP + i + (long)r * nP];
-                        w.i1[r] = (T)0;
-#pragma unroll
-                        for (int cc = 0; cc < NDIM; ++cc) w.iu[r][cc] = (T)0;
-                    }
+                    begin_reverse();
                 } else {
                     if (!BACKWARD) {
 #pragma unroll
@@ -593,12 +600,14 @@ int launch_closednd_forward(int dtype, const Geom& g, int n_theta, long nP, int 
 }
 
 // G [n_theta, D] must be zero-initialised by the caller
+// newpoints: the forward's output if the caller has it (the reverse walk then starts from it), else NULL
 int launch_closednd_backward(int dtype, const Geom& g, int n_theta, long nP, int broadcast, const void* points,
-                             const void* As, const void* gout, void* G, void* dpoints, cudaStream_t st)
+                             const void* As, const void* gout, const void* newpoints, void* G, void* dpoints,
+                             cudaStream_t st)
 {
     if (n_theta == 0 || nP == 0) return kOk;
     const int rf = closed_refill_flag();
-#define GO(T, N) closednd_launch<T, N, true>(g, n_theta, nP, broadcast, points, As, gout, nullptr, G, dpoints, rf, nullptr, st)
+#define GO(T, N) closednd_launch<T, N, true>(g, n_theta, nP, broadcast, points, As, gout, const_cast<void*>(newpoints), G, dpoints, rf, nullptr, st)
     if (g.ndim == 2) return dtype == kF32 ? GO(float, 2) : GO(double, 2);
     return dtype == kF32 ? GO(float, 3) : GO(double, 3);
 #undef GO

@@ -100,7 +100,8 @@ int launch_closed1d_backward(int dtype, const Geom& g, int n_theta, long nP, int
 int launch_closednd_forward(int dtype, const Geom& g, int n_theta, long nP, int broadcast, const void* points,
                             const void* As, void* out, unsigned long long* stats, cudaStream_t st);
 int launch_closednd_backward(int dtype, const Geom& g, int n_theta, long nP, int broadcast, const void* points,
-                             const void* As, const void* gout, void* G, void* dpoints, cudaStream_t st);
+                             const void* As, const void* gout, const void* newpoints, void* G, void* dpoints,
+                             cudaStream_t st);
 void set_closed_refill(int v);
 // cpab_expm.cu
 int launch_theta_to_trels(int dtype, const Geom& g, int nsteps, int n_theta, int d,

@@ -215,9 +215,14 @@ def closed_form_lane_stats(points: torch.Tensor, As: torch.Tensor, nc):
     return out, lanes / max(slots, 1), lanes / max(n_theta * nP, 1)
 
 
-def backward_theta_closed_form(points, As, basis, grad_out, nc, want_dpoints=False):
+def backward_theta_closed_form(points, As, basis, grad_out, nc, want_dpoints=False, newpoints=None):
+    """newpoints: the forward's output, if at hand (2-D / 3-D: spares the kernel its own forward walk)."""
     points, As = _req(points, "points"), _req(As, "As")
     basis, grad_out = _req(basis, "basis"), _req(grad_out, "grad_out")
+    if newpoints is not None:
+        newpoints = _req(newpoints, "newpoints")
+        if newpoints.shape != grad_out.shape or newpoints.dtype != grad_out.dtype:
+            raise ValueError("newpoints must have the shape and dtype of grad_out")
     n_theta = As.shape[0]
     D, d = basis.shape
     broadcast, ndim, nP = _points_layout(points, n_theta)
@@ -228,9 +233,10 @@ def backward_theta_closed_form(points, As, basis, grad_out, nc, want_dpoints=Fal
     dtheta = torch.empty((n_theta, d), dtype=points.dtype, device=points.device)
     dpoints = torch.empty_like(grad_out) if want_dpoints else None
     with torch.cuda.device(points.device):
-        check(lib.cpab_b200_backward_theta_closed_form(
+        check(lib.cpab_b200_backward_theta_closed_form_from(
             code, ndim, nc_array(nc), n_theta, d, nP, broadcast, points.data_ptr(), As.data_ptr(),
-            basis.data_ptr(), grad_out.data_ptr(), dtheta.data_ptr(),
+            basis.data_ptr(), grad_out.data_ptr(), newpoints.data_ptr() if newpoints is not None else None,
+            dtheta.data_ptr(),
             dpoints.data_ptr() if want_dpoints else None, ws.data_ptr(), ws_bytes, _stream()),
             "backward_theta_closed_form")
     return dtheta, dpoints

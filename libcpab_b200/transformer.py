@@ -56,7 +56,10 @@ class _CpabFunction(torch.autograd.Function):
         else:
             newpoints = ops.forward(points, trels, params.nc, params.nstepsolver,
                                     fast_math=bool(getattr(params, "fast_math", False)))
-        ctx.save_for_backward(points, As, B)
+        if ctx.closed_form and params.ndim > 1:       # the hit-time adjoint walks back from the output
+            ctx.save_for_backward(points, As, B, newpoints)
+        else:
+            ctx.save_for_backward(points, As, B)
         ctx.params = params
         ctx.points_need_grad = points.requires_grad and bool(getattr(params, "points_grad", False))
         return newpoints
@@ -64,11 +67,12 @@ class _CpabFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad):
-        points, As, B = ctx.saved_tensors
+        points, As, B = ctx.saved_tensors[:3]
         p = ctx.params
         if ctx.closed_form:
+            x1 = ctx.saved_tensors[3] if len(ctx.saved_tensors) > 3 else None
             dtheta, dpoints = ops.backward_theta_closed_form(points, As, B, grad.contiguous(), p.nc,
-                                                             want_dpoints=ctx.points_need_grad)
+                                                             want_dpoints=ctx.points_need_grad, newpoints=x1)
         else:
             dtheta, dpoints = ops.backward_theta(points, As, B, grad.contiguous(), p.nc, p.nstepsolver,
                                                  want_dpoints=ctx.points_need_grad,

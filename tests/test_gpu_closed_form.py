@@ -199,6 +199,14 @@ def test_nd_gradient_matches_differenced_checker(name, npts):
     interior = ((grid > 1e-3) & (grid < 1 - 1e-3)).all(axis=0)
     print("%s: dpoints vs differenced forward: rel err %.2e" % (name, rel_err(dpts[:, :, interior], fdp[:, :, interior])))
     assert rel_err(dpts[:, :, interior], fdp[:, :, interior]) < 1e-5
+    # the adjoint started from the forward's own output (what autograd does) instead of walking forward first
+    x1 = ops.forward_closed_form(dev(grid), dev(As), nc)
+    dth_x1, dpts_x1 = ops.backward_theta_closed_form(dev(grid), dev(As), dev(B), dev(gout), nc, want_dpoints=True, newpoints=x1)
+    print("%s: dtheta from the saved output vs from the in-kernel forward walk: rel err %.2e" % (name, rel_err(dth_x1.cpu().numpy(), dth)))
+    # (d/dpoints away from the domain boundary: at a vertex of the tessellation that the flow keeps fixed, the
+    # derivative of the flow is one-sided and depends on which of the adjoining simplices the walk starts in)
+    assert rel_err(dth_x1.cpu().numpy(), dth) < 1e-10
+    assert rel_err(dpts_x1.cpu().numpy()[:, :, interior], dpts[:, :, interior]) < 1e-9
     dth32, _ = ops.backward_theta_closed_form(dev(grid, torch.float32), dev(As, torch.float32), dev(B, torch.float32),
                                               dev(gout, torch.float32), nc)
     print("%s: float32 dtheta vs float64: rel err %.2e" % (name, rel_err(dth32.cpu().numpy(), dth)))
@@ -279,6 +287,27 @@ def test_nd_lane_utilisation_with_and_without_refill(nc, size, n_theta):
     assert torch.equal(res[0][0], res[1][0])                 # the same trajectories either way
     assert res[1][1] > res[0][1] and res[1][1] > 0.85
     assert abs(res[0][2] - res[1][2]) < 1e-9
+
+
+@pytest.mark.parametrize("nc", [[3, 3], [2, 2, 2]])
+def test_nd_walk_terminates_on_wild_fields(nc):
+    """Non-finite and absurdly large velocity fields: the sub-step loop has a hard trip-count bound, so the
+    kernel returns (NaN / far-away points are fine, a hang is not)."""
+    from libcpab_b200 import ops
+    n = len(nc)
+    rng = np.random.default_rng(9)
+    grid = rng.uniform(0, 1, size=(n, 96)).astype(np.float32)
+    gout = rng.normal(size=(4, n, 96)).astype(np.float32)
+    As = rng.normal(size=(4, O.n_cells(nc), n, n + 1)).astype(np.float32)
+    As[0] *= 1e6                      # 2e6 sub-steps would be needed: cut off at the bound
+    As[1, 3] = np.nan
+    As[2, 5, 0, 0] = np.inf
+    B = rng.normal(size=(O.n_cells(nc) * n * (n + 1), 5)).astype(np.float32)
+    out = ops.forward_closed_form(dev(grid), dev(As), nc)
+    dth, _ = ops.backward_theta_closed_form(dev(grid), dev(As), dev(B), dev(gout), nc)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (4, n, 96) and tuple(dth.shape) == (4, 5)
+    assert bool(torch.isfinite(out[3]).all()) and bool(torch.isfinite(dth[3]).all())      # the sane theta is untouched
 
 
 def test_closed_form_rejects_bad_arguments():
