@@ -258,16 +258,39 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
     T probe = tau;          // a time just after the crossing: where the trajectory is classified
     int hit = -1;
     if (w.steps < kMaxSubsteps) {
-#pragma unroll 1
+        // Phase 1, the same code for every lane: which faces can be reached at all within the sub-step
+        // (g(t) >= a0 + min(0, a1 t) - sum_{k>=2} |a_k| t^k on [0, tau]).  Most cannot; a lane is usually left
+        // with none or one.  An outer face of the domain is never crossed.
+        unsigned pend = 0u;
+#pragma unroll
         for (int f = 0; f < NF; ++f) {
-            if ((w.closed >> f) & 1u) continue;
-            T n[NDIM], d;
+            T n[NDIM], d, a[K + 1];
             face_of<T, NDIM>(w.typ, f, parity, n, d);
-            // an outer face of the domain is never crossed
             int axis = -1, nz = 0;
 #pragma unroll
             for (int j = 0; j < NDIM; ++j) if (n[j] != (T)0) { axis = j; ++nz; }
-            if (nz == 1 && ((n[axis] > (T)0 && w.idx[axis] == 0) || (n[axis] < (T)0 && w.idx[axis] == g.nc[axis] - 1))) continue;
+            const bool outer = nz == 1 && ((n[axis] > (T)0 && w.idx[axis] == 0) || (n[axis] < (T)0 && w.idx[axis] == g.nc[axis] - 1));
+#pragma unroll
+            for (int k = 0; k <= K; ++k) {
+                T acc = k == 0 ? d + eps : (T)0;
+#pragma unroll
+                for (int j = 0; j < NDIM; ++j) acc = Num<T>::fma(n[j], ck[k][j], acc);
+                a[k] = acc;
+            }
+            T r = fabs(a[K]);
+#pragma unroll
+            for (int k = K - 1; k >= 2; --k) r = Num<T>::fma(r, tau, fabs(a[k]));
+            const bool reach = !(a[0] + fmin((T)0, a[1] * tau) - r * tau * tau > (T)0);
+            if (reach && !outer && !((w.closed >> f) & 1u)) pend |= 1u << f;
+        }
+        // Phase 2: every lane scans ITS reachable faces -- different lanes different faces at the same time, so the
+        // warp iterates as often as its busiest lane has faces (1-2), not once per face of the simplex.
+#pragma unroll 1
+        while (pend != 0u) {
+            const int f = __ffs(pend) - 1;
+            pend &= pend - 1u;
+            T n[NDIM], d;
+            face_of<T, NDIM>(w.typ, f, parity, n, d);
             T a[K + 1];
 #pragma unroll
             for (int k = 0; k <= K; ++k) {
@@ -280,7 +303,7 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
             // just come in through it, started on it, or slides along it) is still inside
             a[0] += eps;
             const T lim = best;
-            {   // cheap exclusion: g(t) >= a0 + min(0, a1 t) - sum_{k>=2} |a_k| t^k on [0, lim]; most faces are out of reach
+            {   // the same exclusion on (0, best]: an earlier face may have shortened the interval
                 T r = fabs(a[K]);
 #pragma unroll
                 for (int k = K - 1; k >= 2; --k) r = Num<T>::fma(r, lim, fabs(a[k]));
