@@ -262,6 +262,7 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
         // (g(t) >= a0 + min(0, a1 t) - sum_{k>=2} |a_k| t^k on [0, tau]).  Most cannot; a lane is usually left
         // with none or one.  An outer face of the domain is never crossed.
         unsigned pend = 0u;
+        T est[NF];      // linear estimate of the hit time: the order in which phase 2 takes the faces
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             T n[NDIM], d, a[K + 1];
@@ -282,13 +283,19 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
             for (int k = K - 1; k >= 2; --k) r = Num<T>::fma(r, tau, fabs(a[k]));
             const bool reach = !(a[0] + fmin((T)0, a[1] * tau) - r * tau * tau > (T)0);
             if (reach && !outer && !((w.closed >> f) & 1u)) pend |= 1u << f;
+            est[f] = a[1] < (T)0 ? a[0] / -a[1] : tau;
         }
         // Phase 2: every lane scans ITS reachable faces -- different lanes different faces at the same time, so the
         // warp iterates as often as its busiest lane has faces (1-2), not once per face of the simplex.
 #pragma unroll 1
         while (pend != 0u) {
-            const int f = __ffs(pend) - 1;
-            pend &= pend - 1u;
+            // nearest first: once its exit is known, the bound on (0, best] usually disposes of the others
+            int f = 0;
+            T e = (T)INFINITY;
+#pragma unroll
+            for (int k = 0; k < NF; ++k)
+                if (((pend >> k) & 1u) && est[k] < e) { e = est[k]; f = k; }
+            pend &= ~(1u << f);
             T n[NDIM], d;
             face_of<T, NDIM>(w.typ, f, parity, n, d);
             T a[K + 1];
@@ -343,8 +350,9 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
                         if (fv > (T)0) lo = tt; else hi = tt;
                         T tn = tt - fv / dv;
                         if (!(tn >= lo && tn <= hi)) tn = (T)0.5 * (lo + hi);
-                        if (tn == tt) break;       // converged (a strict test would bisect away from the root here)
+                        const bool conv = fabs(tn - tt) <= (T)(sizeof(T) == 4 ? 2e-7 : 1e-15) * hi;
                         tt = tn;
+                        if (conv) break;           // (also: a strict interval test would bisect away from a root it sits on)
                     }
                     cand = tt;
                     // classify 4 eps further out (first order), but not later than the node that saw it outside
