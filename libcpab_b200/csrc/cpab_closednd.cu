@@ -96,7 +96,7 @@ template <typename T, int NDIM> struct Walker {
     int idx[NDIM];      // square / cube
     int typ;            // simplex within it
     int steps;
-    unsigned closed;    // faces not tested (a crossing that classified back into this simplex), until time advances
+    unsigned closed;    // faces not tested (found outside one at time 0 but classified into this simplex), until time advances
     // adjoint (reverse walk only)
     T lam[NDIM];                    // dL/dx, global
     T iu[NDIM][NDIM], i1[NDIM];     // int lambda' u^T dr, int lambda' dr over the stay in the current simplex
@@ -355,8 +355,10 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
                         if (conv) break;           // (also: a strict interval test would bisect away from a root it sits on)
                     }
                     cand = tt;
-                    // classify 4 eps further out (first order), but not later than the node that saw it outside
-                    const T dt = (T)4 * eps / fmax(fabs(dv), (T)1e-30);
+                    // go one more eps out (first order; 2 eps behind the face in all: ten times the rounding of the
+                    // classification, and as little of the next simplex's time as possible spent with this one's field),
+                    // but not later than the node that saw it outside
+                    const T dt = eps / fmax(fabs(dv), (T)1e-30);
                     after = cand + dt < t ? cand + dt : t;
                 }
                 tprev = t; fprev = fm; dprev = dm;
@@ -368,7 +370,11 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
             }
         }
     }
-    // advance
+    // advance -- on a crossing to the probe time, a few eps behind the face: the point is then strictly inside the
+    // simplex it is classified into below (also when that is this one again: a trajectory that grazes a face
+    // and comes back just goes on, and a later, real crossing of the same face is seen by the next sub-step)
+    const bool at_once = hit >= 0 && !(probe > (T)0);
+    if (hit >= 0) best = probe;
     T un[NDIM];
 #pragma unroll
     for (int j = 0; j < NDIM; ++j) {
@@ -430,17 +436,13 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
     const bool done = !(w.trem > (T)0);
     if (best > (T)0) w.closed = 0u;
     if (hit >= 0) {
-        // the simplex the trajectory enters: classify the point it reaches just behind the face (followed
-        // with this simplex's own flow -- the fields agree on the face) in the neighbouring cube
+        // the simplex the trajectory is in now: the reference's inequalities in the (neighbouring) cube
         int idx2[NDIM];
         T v[NDIM];
         bool moved = false;
 #pragma unroll
         for (int j = 0; j < NDIM; ++j) {
-            T col[K + 1];
-#pragma unroll
-            for (int k = 0; k <= K; ++k) col[k] = ck[k][j];
-            v[j] = horner<T, K>(col, probe);
+            v[j] = un[j];
             idx2[j] = w.idx[j];
             if (v[j] < (T)0 && idx2[j] > 0) { idx2[j] -= 1; v[j] += (T)1; moved = true; }
             else if (v[j] > (T)1 && idx2[j] < g.nc[j] - 1) { idx2[j] += 1; v[j] -= (T)1; moved = true; }
@@ -452,8 +454,10 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
             for (int j = 0; j < NDIM; ++j) w.idx[j] = idx2[j];
             w.typ = typ2;
             w.closed = 0u;
-        } else {
-            w.closed |= 1u << hit;      // rounding: the probe still classifies into this simplex; go on without this face
+        } else if (at_once) {
+            // found outside a face at the start of the sub-step, yet classified into this simplex (rounding): no
+            // time has passed, so go on without this face until it has
+            w.closed |= 1u << hit;
         }
     }
     if (ADJ && done) flush_cell<T, NDIM>(g, w, Gt, cell_of<T, NDIM>(g, w.idx, w.typ));

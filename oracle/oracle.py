@@ -701,11 +701,13 @@ def closed_form_nd(points: np.ndarray, As: np.ndarray, nc, stats: dict | None = 
                                 t_m, (f_m, d_m) = t_min, face(t_min, p)
                         if f_m < -eps_on:
                             t_p = brentq(lambda t: face(t, p)[0] + eps_on, ts[m - 1], t_m, xtol=1e-15, rtol=1e-15)
-                            after = min(t_m, t_p + 4 * eps_on / max(abs(face(t_p, p)[1]), 1e-300))
+                            after = min(t_m, t_p + eps_on / max(abs(face(t_p, p)[1]), 1e-300))
                             if hit_t is None or t_p < hit_t:
                                 hit_t, hit_p, probe = t_p, p, after
                             break
-                step = tau if hit_t is None else hit_t
+                # on a crossing go to the probe time, a few eps behind the face: strictly inside the simplex the point
+                # is classified into below (also when that is this one again: a graze)
+                step = tau if hit_t is None else probe
                 x_new = (expm(step * At) @ xt)[:ndim]
                 t_rem -= step
                 segs += 1
@@ -724,8 +726,8 @@ def closed_form_nd(points: np.ndarray, As: np.ndarray, nc, stats: dict | None = 
                     typ2 = _simplex_type(ndim, u, int(idx2.sum() & 1) if ndim == 3 else 0)
                     if typ2 != typ or (idx2 != idx).any():
                         idx, typ, closed = idx2, typ2, set()
-                    else:
-                        closed.add(hit_p)
+                    elif not probe > 0:
+                        closed.add(hit_p)      # outside a face at time 0 yet classified into this simplex: rounding
                 x = x_new
                 if t_rem <= 0:
                     break

@@ -264,6 +264,34 @@ def test_nd_api_switch_and_flow_properties(nc, size, n_theta):
     assert tuple(img.shape) == tuple(data.shape) and bool(torch.isfinite(img).all())
 
 
+@pytest.mark.parametrize("nc,size,n_theta", [([10, 10], [512, 512], 8), ([4, 4, 4], [80, 80, 80], 4)])
+def test_nd_float32_agrees_with_float64_at_scale(nc, size, n_theta):
+    """Millions of trajectories, theta ~ N(0, I): the float32 kernels against the float64 ones (which the small
+    cases hold to the checker) -- the net for rare paths (vertices, grazing faces, dips between scan nodes)."""
+    from libcpab_b200 import Cpab, ops
+    torch.manual_seed(5)
+    T = Cpab(nc, backend="pytorch", device="gpu")
+    theta = T.sample_transformation(n_theta).double()
+    grid = T.uniform_meshgrid(size).double()
+    B = torch.as_tensor(np.asarray(T.params.basis), dtype=torch.float64, device="cuda")
+    As = (B @ theta.T).T.reshape(n_theta, -1, len(nc), len(nc) + 1).contiguous()
+    gout = torch.randn(n_theta, len(nc), grid.shape[1], dtype=torch.float64, device="cuda")
+    x64 = ops.forward_closed_form(grid, As, nc)
+    x32 = ops.forward_closed_form(grid.float(), As.float(), nc)
+    err = (x32.double() - x64).abs().amax(dim=1)
+    gain = flow_gain(As.cpu().numpy())
+    print("nc %s: %d trajectories, float32 vs float64 max %.2e, 99.99th percentile %.2e (flow gain %.1f)"
+          % (nc, err.numel(), float(err.max()), float(err.flatten().kthvalue(int(err.numel() * 0.9999)).values), gain))
+    assert float(err.max()) < 1e-6 * gain + 5e-6
+    d64, _ = ops.backward_theta_closed_form(grid, As, B, gout, nc, newpoints=x64)
+    d32, _ = ops.backward_theta_closed_form(grid.float(), As.float(), B.float(), gout.float(), nc, newpoints=x32)
+    e = theta_rel = ((d32.double() - d64).abs().amax(dim=1) / d64.abs().amax(dim=1))
+    print("nc %s: dtheta float32 vs float64, per theta: max %.2e median %.2e" % (nc, float(e.max()), float(e.median())))
+    assert float(e.max()) < 1e-3        # (the reference's own float32 and float64 gradients differ by 9e-4 on BASELINE configs[0])
+    back = ops.forward_closed_form(x64, -As, nc)                      # the flow of -theta undoes it
+    assert float((back - grid[None]).abs().max()) < 1e-10
+
+
 @pytest.mark.parametrize("nc,size,n_theta", [([10, 10], [256, 256], 32), ([4, 4, 4], [64, 64, 64], 4)])
 def test_nd_lane_utilisation_with_and_without_refill(nc, size, n_theta):
     """Divergence of the crossing loop, measured: share of the warps' loop slots that do work."""

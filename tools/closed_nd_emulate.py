@@ -82,12 +82,14 @@ def walk(x, As, nc, verbose=False):
                         if tn == tt: break
                         tt = tn
                     cand = tt
-                    dt = 4 * eps / max(abs(dv), 1e-30)
+                    dt = eps / max(abs(dv), 1e-30)
                     after = cand + dt if cand + dt < t else t
                 tprev, fprev, dprev = t, fm, dm
                 m += 1
             if found and (cand < best or hit < 0):
                 best = min(cand, best); probe = after; hit = f
+        at_once = hit >= 0 and not (probe > 0)
+        if hit >= 0: best = probe
         tpow = best ** np.arange(K + 1)
         un = tpow @ ck
         x = (idx + un) / ncv
@@ -96,7 +98,7 @@ def walk(x, As, nc, verbose=False):
         done = not (trem > 0)
         if best > 0: closed = 0
         if hit >= 0:
-            v = (probe ** np.arange(K + 1)) @ ck
+            v = un.copy()
             idx2 = idx.copy(); moved = False
             for j in range(ndim):
                 if v[j] < 0 and idx2[j] > 0: idx2[j] -= 1; v[j] += 1; moved = True
@@ -104,7 +106,7 @@ def walk(x, As, nc, verbose=False):
             typ2 = OO._simplex_type(ndim, v, int(idx2.sum() & 1) if ndim == 3 else 0)
             if moved or typ2 != typ:
                 idx, typ, closed = idx2, typ2, 0
-            else:
+            elif at_once:
                 closed |= 1 << hit
                 if verbose: print("    closed", hit)
         if done or steps > 2000: break
