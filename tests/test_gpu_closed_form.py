@@ -290,6 +290,23 @@ def test_nd_float32_agrees_with_float64_at_scale(nc, size, n_theta):
     assert float(e.max()) < 1e-3        # (the reference's own float32 and float64 gradients differ by 9e-4 on BASELINE configs[0])
     back = ops.forward_closed_form(x64, -As, nc)                      # the flow of -theta undoes it
     assert float((back - grid[None]).abs().max()) < 1e-10
+    # the adjoint over all these trajectories against central differences of the float64 forward, random directions
+    for k in range(2):
+        dirn = torch.randn_like(theta)
+        # (the flow is C1 in theta with a kink in its second derivative at every change of a cell sequence; summed over
+        #  2e6 trajectories the central difference is only good to ~1e-5 relative in 2-D -- it moves by 1.3e-4 between
+        #  eps = 1e-6 and 1e-5, and a Richardson step does not cure it; the 64-point cases above hold the adjoint to 1e-9)
+        eps = 1e-6
+
+        def loss(th):
+            A = (B @ th.T).T.reshape(n_theta, -1, len(nc), len(nc) + 1).contiguous()
+            return float((ops.forward_closed_form(grid, A, nc) * gout).sum())
+
+        fd = (loss(theta + eps * dirn) - loss(theta - eps * dirn)) / (2 * eps)
+        an = float((d64 * dirn).sum())
+        print("nc %s: directional derivative over %d trajectories: adjoint %.10e, differenced forward %.10e"
+              % (nc, err.numel(), an, fd))
+        assert abs(an - fd) < 1e-5 * max(1.0, abs(fd))
 
 
 @pytest.mark.parametrize("nc,size,n_theta", [([10, 10], [256, 256], 32), ([4, 4, 4], [64, 64, 64], 4)])
