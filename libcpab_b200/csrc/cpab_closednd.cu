@@ -16,14 +16,19 @@
 //     truncated below the rounding of T after K = 8 (float) / 14 (double) terms).  A sub-step that
 //     reaches no face just continues in the same simplex; the composition is still the exact flow.
 //   * Hit time: every face f (3 per triangle, 4 per tetrahedron; tables below, inward positive) is
-//     the polynomial g_f(t) = n_f . u(t) + d_f.  It is sampled at 4 nodes of the sub-step; the
-//     first node at which it is negative after having been positive brackets the exit, which a
-//     safeguarded Newton iteration on the polynomial refines.  A face on which the point lies
-//     (|g| <= eps: it has just come in through it, it started on it, or it slides along it) is
-//     crossed at once if g turns negative without having been positive.  The hit time has no closed
-//     form in more than one dimension (a sum of exponentials); the polynomial is its series.
-//   * Crossing: the hit point, nudged through the face, is classified in the neighbouring cube's
-//     local coordinates by the reference's own inequalities (cpab_ops.cpp:94-103, :160-184).  Outer
+//     the polynomial g_f(t) = n_f . u(t) + d_f + eps; the exit is the first time it turns negative (a
+//     point within eps of a face -- it has just come in through it, it started on it, or it slides
+//     along it -- counts as inside).  Phase 1, the same code for every lane: faces that cannot be
+//     reached within the sub-step are excluded by a bound on the polynomial (most are).  Phase 2,
+//     per lane over its reachable faces, nearest first: the polynomial at 4 nodes of the sub-step
+//     (plus a search for a minimum between two nodes where its derivative changes sign: a
+//     trajectory that dips through the face and returns), the first sign change refined by
+//     safeguarded Newton.  The hit time has no closed form in more than one dimension (a sum of
+//     exponentials); the polynomial is its series.
+//   * Crossing: the walk advances to a point 2 eps behind the face (first order; the fields of the
+//     two simplices agree on the face) and classifies it in the neighbouring cube's local
+//     coordinates by the reference's own inequalities (cpab_ops.cpp:94-103, :160-184).  A
+//     trajectory that only grazes the face classifies back into its own simplex and goes on.  Outer
 //     faces of the domain are never crossed: outside the unit box (tessellations without zero
 //     boundary) the boundary cubes' planes are simply continued.
 // The loop runs once per sub-step; its trip count varies per trajectory (crossings + ||L|| / rho).
@@ -35,8 +40,9 @@
 // crossing (the jump would be (v- - v+) dt*/dtheta = 0): the exact gradient is the in-cell
 // variational equation integrated piecewise, in adjoint form
 //     dL/dtheta = sum_c <B_c, G_c>,   G_c = int_{t: x(t) in c} lambda(t) [x(t); 1]^T dt,   lambda' = -L_c^T lambda.
-// The backward kernel first walks forward to x(1) (or takes x(1) from the caller), then walks the REVERSED field (-A) back from
-// x(1) -- the same hit-time code, the same cells in reverse order up to rounding, no trajectory
+// The backward kernel takes x(1) from the caller (autograd has it; a kernel that walks forward to it first
+// has lanes in both phases at once and pays for both code paths: 2.4x slower) and walks the REVERSED field
+// (-A) back from there -- the same hit-time code, the same cells in reverse order up to rounding, no trajectory
 // storage -- carrying lambda'(r) = expm(r L'^T) lambda' as a second Taylor polynomial and adding
 // int lambda u^T dr per sub-step by Gauss-Legendre quadrature (3 / 8 nodes).  G goes through the same
 // G.B epilogue as the fixed-step adjoint; lambda at t = 0 is dL/dpoints.
