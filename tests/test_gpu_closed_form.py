@@ -355,6 +355,41 @@ def test_nd_walk_terminates_on_wild_fields(nc):
     assert bool(torch.isfinite(out[3]).all()) and bool(torch.isfinite(dth[3]).all())      # the sane theta is untouched
 
 
+def test_nd_sequential_chain_trains_every_warp_exactly():
+    """CpabSequential of two 2-D hit-time flows with params.points_grad: the gradient reaches the first warp through
+    lambda(0) of the second (dL/dpoints of the adjoint).  Both thetas against central differences of the chain, float64."""
+    from libcpab_b200 import Cpab, CpabSequential
+    g = load_golden("d2_t3x3")
+    Ts = [Cpab([3, 3], backend="pytorch", device="gpu", basis=g["B"]) for _ in range(2)]
+    for T in Ts:
+        T.params.closed_form = True
+        T.params.points_grad = True
+    S = CpabSequential(*Ts)
+    torch.manual_seed(2)
+    thetas = [(0.6 * torch.as_tensor(g["theta"][k:k + 2], dtype=torch.float64)).cuda().requires_grad_(True) for k in (0, 2)]
+    grid = torch.rand(2, 300, dtype=torch.float64, device="cuda") * 0.98 + 0.01
+    R = torch.randn(2, 2, 300, dtype=torch.float64, device="cuda")
+
+    def loss(ths):
+        return (S.transform_grid(grid, ths) * R).sum()
+
+    loss(thetas).backward()
+    rng = np.random.default_rng(0)
+    for w in range(2):
+        assert thetas[w].grad is not None
+        for _ in range(3):
+            dirn = torch.as_tensor(rng.normal(size=tuple(thetas[w].shape)), device="cuda")
+            eps = 1e-6
+            plus = [t.detach().clone() for t in thetas]
+            minus = [t.detach().clone() for t in thetas]
+            plus[w] += eps * dirn
+            minus[w] -= eps * dirn
+            fd = float(loss(plus) - loss(minus)) / (2 * eps)
+            an = float((thetas[w].grad * dirn).sum())
+            print("warp %d: directional derivative %.9e, differenced chain %.9e" % (w, an, fd))
+            assert abs(an - fd) < 1e-6 * max(1.0, abs(fd))
+
+
 def test_closed_form_rejects_bad_arguments():
     from libcpab_b200 import _lib, ops
     with pytest.raises(_lib.CpabError):
