@@ -67,7 +67,7 @@ const char* cpab_b200_last_error(void);
 const char* cpab_b200_build_info(void);
 
 /* Experiment knobs, per calling thread ("fwd_ppt", "chunk_pts", "chunk_auto", "bwd_seg", "bwd_stage",
- * "bwd_block", "interp_variant" 0-11, "interp_max_ctas"); results never depend on them beyond
+ * "bwd_block", "interp_variant" 0-11, "interp_max_ctas", "closed_refill", "closed_stage"); results never depend on them beyond
  * floating-point summation order in the gradient.  ("interp_variant" 12-15 are measurement probes of
  * the interpolate forward that deliberately skip work: tools/interp_variants.py only.) */
 int cpab_b200_set_tuning(const char* key, int value);

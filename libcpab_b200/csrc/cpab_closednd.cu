@@ -593,13 +593,25 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     }
 }
 
+int& closed_refill_flag()
+{
+    thread_local int v = 1;
+    return v;
+}
+int& closed_stage_flag()
+{
+    thread_local int v = 1;
+    return v;
+}
+
+
 template <typename T, int NDIM, bool BACKWARD>
 int closednd_launch(const Geom& g, int n_theta, long nP, int broadcast, const void* points, const void* As,
                     const void* gout, void* out, void* G, void* dpoints, int refill, unsigned long long* stats,
                     cudaStream_t st)
 {
     const size_t table = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
-    const int staged = table <= 96 * 1024;
+    const int staged = table <= 96 * 1024 && closed_stage_flag() != 0;      // else: the matrices through L1 (large tessellations)
     const size_t smem = staged ? table : 0;
     int chunk_pts = 1024;
     // few thetas: cut finer so that the grid fills the chip
@@ -619,15 +631,10 @@ int closednd_launch(const Geom& g, int n_theta, long nP, int broadcast, const vo
     return kOk;
 }
 
-int& closed_refill_flag()
-{
-    thread_local int v = 1;
-    return v;
-}
-
 }  // namespace
 
 void set_closed_refill(int v) { closed_refill_flag() = v; }
+void set_closed_stage(int v) { closed_stage_flag() = v; }
 
 int launch_closednd_forward(int dtype, const Geom& g, int n_theta, long nP, int broadcast, const void* points,
                             const void* As, void* out, unsigned long long* stats, cudaStream_t st)

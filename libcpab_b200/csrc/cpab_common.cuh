@@ -103,6 +103,7 @@ int launch_closednd_backward(int dtype, const Geom& g, int n_theta, long nP, int
                              const void* As, const void* gout, const void* newpoints, void* G, void* dpoints,
                              cudaStream_t st);
 void set_closed_refill(int v);
+void set_closed_stage(int v);
 // cpab_expm.cu
 int launch_theta_to_trels(int dtype, const Geom& g, int nsteps, int n_theta, int d,
                           const void* basis_t, const void* theta, void* As, void* trels,

@@ -337,6 +337,7 @@ int set_tuning(const char* key, int value)
     if (k == "interp_variant" && value >= 0 && value <= 15) { set_interp_variant(value); return kOk; }
     if (k == "interp_max_ctas" && value >= 0) { set_interp_max_ctas(value); return kOk; }
     if (k == "closed_refill" && (value == 0 || value == 1)) { set_closed_refill(value); return kOk; }
+    if (k == "closed_stage" && (value == 0 || value == 1)) { set_closed_stage(value); return kOk; }
     set_error("unknown tuning key/value %s=%d", key, value);
     return kErrArgument;
 }

@@ -390,6 +390,27 @@ def test_nd_sequential_chain_trains_every_warp_exactly():
             assert abs(an - fd) < 1e-6 * max(1.0, abs(fd))
 
 
+@pytest.mark.parametrize("name", ["d2_t10x10_vp", "d3_t2x2x2"])
+def test_nd_unstaged_tables_give_the_same_result(name):
+    """Tessellations whose velocity matrices do not fit shared memory read them through L1; forced here with
+    the tuning key "closed_stage" = 0: identical trajectories and gradients."""
+    from libcpab_b200 import _lib, ops
+    g, nc, theta, As, grid = _nd_case(name, 400)
+    rng = np.random.default_rng(8)
+    gout = rng.normal(size=(theta.shape[0], len(nc), grid.shape[1]))
+    res = []
+    try:
+        for stage in (1, 0):
+            _lib.set_tuning("closed_stage", stage)
+            x = ops.forward_closed_form(dev(grid, torch.float32), dev(As, torch.float32), nc)
+            d, _ = ops.backward_theta_closed_form(dev(grid), dev(As), dev(g["B"]), dev(gout), nc)
+            res.append((x, d))
+    finally:
+        _lib.set_tuning("closed_stage", 1)
+    assert torch.equal(res[0][0], res[1][0])
+    assert rel_err(res[1][1].cpu().numpy(), res[0][1].cpu().numpy()) < 1e-12      # (atomics: summation order)
+
+
 def test_closed_form_rejects_bad_arguments():
     from libcpab_b200 import _lib, ops
     with pytest.raises(_lib.CpabError):
