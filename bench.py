@@ -725,7 +725,8 @@ def closed_form_records(ctx, steps):
     from libcpab_b200 import Cpab, _lib, ops
     torch = ctx.torch
     out = {}
-    for name, tess, n_theta, size, kw in (("2d_t10x10vp_b64_512x512", [10, 10], 64, [512, 512], {"volume_perservation": True}),
+    for name, tess, n_theta, size, kw in (("1d_t100_b8192_1024", [100], 8192, [1024], {}),
+                                          ("2d_t10x10vp_b64_512x512", [10, 10], 64, [512, 512], {"volume_perservation": True}),
                                           ("3d_t4x4x4_b16_128cubed", [4, 4, 4], 16, [128, 128, 128], {})):
         torch.manual_seed(77)
         T = Cpab(tess, backend="pytorch", device="gpu", **kw)
@@ -755,6 +756,11 @@ def closed_form_records(ctx, steps):
         fixed = T.transform_grid(grid, theta.detach())
         inner = (grid < 1).all(dim=0)
         rec["max_abs_diff_fixed_step_vs_hit_time"] = float((exact - fixed)[:, :, inner].abs().max())
+        if len(tess) == 1:          # (the 1-D walk has a closed-form hit time and no lane refill)
+            out[name] = rec
+            del theta, grid, R
+            torch.cuda.empty_cache()
+            continue
         B = torch.as_tensor(np.asarray(T.params.basis), dtype=torch.float32, device=ctx.dev)
         As = (B @ theta.detach().T).T.reshape(n_theta, -1, len(tess), len(tess) + 1).contiguous()
         util = {}
