@@ -613,7 +613,11 @@ int closednd_launch(const Geom& g, int n_theta, long nP, int broadcast, const vo
     const size_t table = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
     const int staged = table <= 96 * 1024 && closed_stage_flag() != 0;      // else: the matrices through L1 (large tessellations)
     const size_t smem = staged ? table : 0;
-    int chunk_pts = 1024;
+    // points per CTA (a quarter of it per warp): the longer a warp's range, the shorter the share of its refill loop
+    // spent with idle lanes at the end (lane utilisation 0.91 / 0.96 / 0.98 at 1024 / 2048 / 4096).  Measured, 2-D / 3-D:
+    // forward 1.67 / 6.53 ms at 1024, 1.61 / 6.61 at 2048, 1.69 / 6.75 at 4096; backward 2.39 / 13.2 at 1024,
+    // 2.20 / 9.9 at 4096, 2.51 / 10.3 at 8192
+    int chunk_pts = BACKWARD ? 4096 : 2048;
     // few thetas: cut finer so that the grid fills the chip
     while (chunk_pts > 128 && (long long)n_theta * ((nP + chunk_pts - 1) / chunk_pts) < 4LL * sm_count()) chunk_pts /= 2;
     const long chunks = (nP + chunk_pts - 1) / chunk_pts;
