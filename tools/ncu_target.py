@@ -31,8 +31,8 @@ g2 = torch.randn_like(data)
 for _ in range(reps):
     As, Tr = ops.theta_to_trels(theta, Bt, tess, 50)
     if which == "1d" or "closed" in sys.argv:
-        ops.forward_closed_form(grid, As, tess)
-        ops.backward_theta_closed_form(grid, As, B, gout, tess)
+        x1 = ops.forward_closed_form(grid, As, tess)
+        ops.backward_theta_closed_form(grid, As, B, gout, tess, newpoints=x1 if which != "1d" else None)   # as autograd calls it
     gt = ops.forward(grid, Tr, tess, 50)
     out = ops.interpolate_forward(data, gt, size)
     ops.interpolate_backward(data, gt, g2, True, False)
