@@ -136,13 +136,17 @@ template <typename T, int NDIM> __device__ __forceinline__ int simplex_type(cons
 }
 
 // face f of simplex `typ`: normal and offset in the cube's own (unrotated) local coordinates
-template <typename T, int NDIM> __device__ __forceinline__ void face_of(int typ, int f, int parity, T* n, T& d)
+// (`tbl`: the kernel's shared-memory copy of the table -- lanes sit in different simplices, and a constant-bank
+//  load with 32 different addresses is replayed per address)
+template <typename T, int NDIM> __device__ __forceinline__ void face_of(const float* tbl, int typ, int f, int parity, T* n, T& d)
 {
     if (NDIM == 2) {
-        n[0] = (T)c_faces2[typ][f][0]; n[1] = (T)c_faces2[typ][f][1]; d = (T)c_faces2[typ][f][2];
+        const float* r = tbl + (typ * 3 + f) * 3;
+        n[0] = (T)r[0]; n[1] = (T)r[1]; d = (T)r[2];
     } else {
-        const T a = (T)c_faces3[typ][f][0], b = (T)c_faces3[typ][f][1], c = (T)c_faces3[typ][f][2];
-        d = (T)c_faces3[typ][f][3];
+        const float* r = tbl + (typ * 4 + f) * 4;
+        const T a = (T)r[0], b = (T)r[1], c = (T)r[2];
+        d = (T)r[3];
         if (parity) { n[0] = -b; n[1] = a; d += b; }     // a x' + b y' + c z + d,  x' = y, y' = 1 - x
         else { n[0] = a; n[1] = b; }
         n[NDIM - 1] = c;
@@ -165,6 +169,7 @@ template <typename T, int K> __device__ __forceinline__ void horner2(const T* a,
 
 template <typename T, int NDIM> struct CfTable {      // velocity matrices of one theta: shared memory or global
     const T* A;
+    const float* faces;     // shared-memory copy of c_faces2 / c_faces3
     __device__ __forceinline__ void load(int c, T* a) const
     {
 #pragma unroll
@@ -272,7 +277,7 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             T n[NDIM], d, a[K + 1];
-            face_of<T, NDIM>(w.typ, f, parity, n, d);
+            face_of<T, NDIM>(tab.faces, w.typ, f, parity, n, d);
             int axis = -1, nz = 0;
 #pragma unroll
             for (int j = 0; j < NDIM; ++j) if (n[j] != (T)0) { axis = j; ++nz; }
@@ -303,7 +308,7 @@ __device__ __noinline__ bool substep(const Geom& g, const CfTable<T, NDIM>& tab,
                 if (((pend >> k) & 1u) && est[k] < e) { e = est[k]; f = k; }
             pend &= ~(1u << f);
             T n[NDIM], d;
-            face_of<T, NDIM>(w.typ, f, parity, n, d);
+            face_of<T, NDIM>(tab.faces, w.typ, f, parity, n, d);
             T a[K + 1];
 #pragma unroll
             for (int k = 0; k <= K; ++k) {
@@ -508,6 +513,11 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     const int chunk = blockIdx.x - theta * chunks;
     const T* Ag = As + (size_t)theta * g.n_cells * PPC;
     CfTable<T, NDIM> tab;
+    __shared__ float s_faces[NDIM == 2 ? 36 : 80];
+    for (int i = threadIdx.x; i < (NDIM == 2 ? 36 : 80); i += blockDim.x)
+        s_faces[i] = NDIM == 2 ? (&c_faces2[0][0][0])[i] : (&c_faces3[0][0][0])[i];
+    tab.faces = s_faces;
+    if (!staged) __syncthreads();
     if (staged) {
         T* sA = reinterpret_cast<T*>(smem_raw);
         for (int i = threadIdx.x; i < g.n_cells * PPC; i += blockDim.x) sA[i] = Ag[i];
