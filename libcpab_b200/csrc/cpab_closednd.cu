@@ -94,6 +94,7 @@ template <> struct Cf<double> {
     }
 };
 
+constexpr int kRing = 128;              // points a warp keeps prefetched in shared memory
 constexpr int kMaxSubsteps = 1 << 14;     // guard: after this many sub-steps the faces are no longer tested
 
 template <typename T, int NDIM> struct Walker {
@@ -518,8 +519,9 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
         s_faces[i] = NDIM == 2 ? (&c_faces2[0][0][0])[i] : (&c_faces3[0][0][0])[i];
     tab.faces = s_faces;
     if (!staged) __syncthreads();
+    constexpr int NV = BACKWARD ? 2 * NDIM : NDIM;
     if (staged) {
-        T* sA = reinterpret_cast<T*>(smem_raw);
+        T* sA = reinterpret_cast<T*>(smem_raw) + (size_t)4 * kRing * NV;
         for (int i = threadIdx.x; i < g.n_cells * PPC; i += blockDim.x) sA[i] = Ag[i];
         __syncthreads();
         tab.A = sA;
@@ -539,7 +541,29 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     if (NDIM == 3 && g.nc[2] > nmax) nmax = g.nc[2];
     const T eps = Cf<T>::kEps * (T)nmax;
 
+    // ---- prefetch ring of this warp: slot (i & 127) of value v at ringw[v * kRing + slot]
+    T* ringw = reinterpret_cast<T*>(smem_raw) + (size_t)warp * kRing * NV;
+    const bool from_x1 = BACKWARD && out != nullptr;     // backward with the forward's output at hand (`out`, an input then)
+    long loaded = next;                                   // points [next, loaded) are in the ring (or on their way)
+    auto issue_group = [&]() {
+        const long pi = loaded + lane;
+        if (pi < wend) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const T* gp = v < NDIM ? (from_x1 ? out + (size_t)theta * NDIM * nP + pi + (long)v * nP : src + pi + (long)v * nP)
+                                       : gout + (size_t)theta * NDIM * nP + pi + (long)(v - NDIM) * nP;
+                const uint32_t sp = (uint32_t)__cvta_generic_to_shared(ringw + v * kRing + (int)(pi & (kRing - 1)));
+                if (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sp), "l"(gp) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp), "l"(gp) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        loaded += 32;
+    };
+    issue_group(); issue_group(); issue_group(); issue_group();      // (beyond wend: empty groups)
+
     Walker<T, NDIM> w;
+    T lam0[NDIM];           // upstream gradient of the lane's trajectory (backward), taken from the ring at the refill
     bool active = false, reverse = false;
     long i = 0;
     auto begin_reverse = [&]() {
@@ -548,7 +572,7 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
         w.closed = 0u;
 #pragma unroll
         for (int r = 0; r < NDIM; ++r) {
-            w.lam[r] = BACKWARD ? gout[(size_t)theta * NDIM * nP + i + (long)r * nP] : (T)0;
+            w.lam[r] = BACKWARD ? lam0[r] : (T)0;
             w.i1[r] = (T)0;
 #pragma unroll
             for (int cc = 0; cc < NDIM; ++cc) w.iu[r][cc] = (T)0;
@@ -556,16 +580,26 @@ k_closednd(const T* __restrict__ points, const T* __restrict__ As, const T* __re
     };
     unsigned long long lane_steps = 0, warp_iters = 0;
     for (;;) {
+        // keep the ring at least 64 points ahead (one group per iteration is as fast as the lanes can consume):
+        // what a refill reads then always belongs to a group older than the newest one
+        bool issued = false;
+        if (loaded < wend && loaded - next <= kRing - 32) { issue_group(); issued = true; }
         if (refill || !__any_sync(full, active)) {
             const unsigned m = __ballot_sync(full, !active);
             const long ni = next + __popc(m & ((1u << lane) - 1u));
+            if (m != 0u) {
+                if (issued) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();          // the copies of every lane are visible to every lane
+            }
             if (!active && ni < wend) {
                 i = ni;
-                // backward with the forward's output at hand (`out`, an input then): start the reverse walk there
-                const bool from_x1 = BACKWARD && out != nullptr;
+                const int slot = (int)(i & (kRing - 1));
 #pragma unroll
-                for (int j = 0; j < NDIM; ++j)
-                    w.x[j] = from_x1 ? out[(size_t)theta * NDIM * nP + i + (long)j * nP] : src[i + (long)j * nP];
+                for (int j = 0; j < NDIM; ++j) {
+                    w.x[j] = ringw[j * kRing + slot];
+                    if (BACKWARD) lam0[j] = ringw[(NDIM + j) * kRing + slot];
+                }
                 start_walk<T, NDIM>(g, w);
                 reverse = from_x1;
                 if (from_x1) begin_reverse();
@@ -622,7 +656,11 @@ int closednd_launch(const Geom& g, int n_theta, long nP, int broadcast, const vo
 {
     const size_t table = (size_t)g.n_cells * Dim<NDIM>::kPpc * sizeof(T);
     const int staged = table <= 96 * 1024 && closed_stage_flag() != 0;      // else: the matrices through L1 (large tessellations)
-    const size_t smem = staged ? table : 0;
+    // per warp: a ring of the next 128 points' inputs (start point; backward: the upstream gradient too), filled by
+    // cp.async three groups ahead of the lane refills that consume it -- a refill that loads from global memory
+    // stalls its whole warp on every loop iteration in which some lane finishes, i.e. on nearly every one
+    const size_t ring = (size_t)4 * kRing * (BACKWARD ? 2 * NDIM : NDIM) * sizeof(T);
+    const size_t smem = ring + (staged ? table : 0);
     // points per CTA (a quarter of it per warp): the longer a warp's range, the shorter the share of its refill loop
     // spent with idle lanes at the end (lane utilisation 0.91 / 0.96 / 0.98 at 1024 / 2048 / 4096).  Measured, 2-D / 3-D:
     // forward 1.67 / 6.53 ms at 1024, 1.61 / 6.61 at 2048, 1.69 / 6.75 at 4096; backward 2.39 / 13.2 at 1024,
